@@ -1,0 +1,215 @@
+/*
+ * rt_b200.h — C-ABI of the B200-native render hot path (librt_b200.so).
+ *
+ * The reference (deluf/parallel-ray-tracer) has no plugin/FFI interface: its render call
+ * is a set of free functions over process-wide globals.  The shape this header makes
+ * explicit and re-entrant is the reference GPU program's triple
+ *
+ *      void  load_to_gpu();                                  gpu/include/gpu.cuh:24, gpu/src/gpu.cu:129-201
+ *      float render_frame(bool is_metrics, int tx, int ty);  gpu/include/gpu.cuh:23, gpu/src/gpu.cu:98-127
+ *      void  load_from_gpu();                                gpu/include/gpu.cuh:25, gpu/src/gpu.cu:203-228
+ *
+ * (CPU program: `void render_frame()` over the same globals, cpu/src/main.c:42,214-226.)
+ * Each export below cites the reference interface it replaces.  Only plain pointers and
+ * sizes cross the boundary; no CUDA, torch or C++ types.  Every function returns 0 on
+ * success or a negative rt_status; nothing in the library calls exit() (the reference
+ * does, cpu/src/triangle.c:28-31).  There is NO CPU fallback: without a CUDA device
+ * rt_create fails with RT_ERR_NO_DEVICE.
+ *
+ * Threading: calls on one rt_ctx must not be concurrent; distinct contexts are independent
+ * (the reference keeps device pointers in __constant__ symbols, one scene per process).
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_B200_ABI_VERSION 1
+#define RT_MAX_DEVICES 16
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,    /* bad argument */
+    RT_ERR_IO = -2,         /* file missing / malformed */
+    RT_ERR_NO_DEVICE = -3,  /* no usable CUDA device (there is no CPU fallback) */
+    RT_ERR_CUDA = -4,       /* a CUDA runtime call failed; see rt_last_error */
+    RT_ERR_NOMEM = -5,
+    RT_ERR_STATE = -6       /* call order (e.g. download before render) */
+} rt_status;
+
+/* ------------------------------------------------------------------------------------
+ * Host scene — the reference's L2 "scene prep" results, as plain arrays.
+ * ------------------------------------------------------------------------------------ */
+
+/* One BVH node exactly as the reference stores it (cpu/include/bvh.h:9-23, 32 bytes):
+ * leaf iff tr_len > 0 (triangles tri_idx[idx .. idx+tr_len)); inner iff tr_len == 0 and
+ * idx != 0 (children idx, idx+1); tr_len == 0 && idx == 0 is an empty leaf. */
+typedef struct rt_bvh_node {
+    float   min[3];
+    float   max[3];
+    int32_t tr_len;
+    int32_t idx;
+} rt_bvh_node;
+
+/* Borrowed view of a scene in the reference's host layout.  All pointers are caller-owned
+ * and only read during the call they are passed to. */
+typedef struct rt_scene_desc {
+    const float*       tri_coords;  /* n_tris x 9: v0 v1 v2 (triangle_t.coords, cpu/include/triangle.h:9) */
+    const uint32_t*    tri_mat;     /* n_tris material indices (mat_idx, gpu/include/triangle.cuh) */
+    uint32_t           n_tris;      /* triangle index = OBJ face order = first-hit ID space */
+    const float*       materials;   /* n_mats x 9: ks kd kr (cpu/include/triangle.h:11-13) */
+    uint32_t           n_mats;
+    const float*       lights;      /* n_lights x 6: pos kl (cpu/include/light.h:8-11) */
+    uint32_t           n_lights;
+    float              ambient[3];  /* amb_light, cpu/src/main.c:37 */
+    const rt_bvh_node* bvh;         /* bvh_len nodes as built by bvh_build (cpu/src/bvh.c:360-388) */
+    const int32_t*     tri_idx;     /* n_tris leaf-order permutation (cpu/src/bvh.c:17) */
+    uint32_t           bvh_len;
+} rt_scene_desc;
+
+/* Library-owned host scene: loaders + host BVH build (C++), replacing
+ * triangles_load/lights_load (cpu/src/triangle.c:74-126, cpu/src/light.c:6-29) and
+ * bvh_build (cpu/src/bvh.c:360-388). */
+typedef struct rt_scene rt_scene;
+
+/* Parse OBJ/MTL/lights files with the reference loader's rules.  Material
+ * fields a .mtl block does not set are zero (the reference leaves them uninitialised). */
+int rt_scene_load_obj(const char* obj_path, const char* mtl_path, const char* lights_path, rt_scene** out);
+/* Same, from DIR/triangles.obj, DIR/triangles.mtl, DIR/lights.obj (cpu/src/main.c:113-114). */
+int rt_scene_load_dir(const char* dir, rt_scene** out);
+/* Binary scene pack ".rtsc": "RTSC0001", u32 n_tris,n_mats,n_lights,0, f32 ambient[3],0,
+ * f32 tri[n_tris][9], u32 mat_idx[n_tris], f32 mats[n_mats][9], f32 lights[n_lights][6]. */
+int rt_scene_load_rtsc(const char* path, rt_scene** out);
+int rt_scene_save_rtsc(const rt_scene* s, const char* path);
+/* Copy caller arrays (desc->bvh may be NULL). */
+int rt_scene_from_arrays(const rt_scene_desc* desc, rt_scene** out);
+/* The reference's synthetic triangle soup (cpu/src/main.c:115-131) driven by libc
+ * srand(seed)/rand(): a in [-5,5)^3, b = a+U[0,1)^3, c = b+U[0,1)^3, ks=1, kd=kr=0, no lights. */
+int rt_scene_soup(uint32_t n_tris, uint32_t seed, rt_scene** out);
+/* base instanced on an nx*ny*nz grid with the given pitch (scale kept: SURVEY.md §A.3b);
+ * lights are replicated every `light_every` instances (0 = keep base lights only). */
+int rt_scene_instance_grid(const rt_scene* base, uint32_t nx, uint32_t ny, uint32_t nz,
+                           const float pitch[3], uint32_t light_every, rt_scene** out);
+/* Host BVH build reproducing the reference tree node for node.  heuristic: 6 (binned
+ * squared-diagonal "SAH", 32 bins; gpu/include/options.cuh:50), 0 or 1 (spatial median,
+ * cpu/src/bvh.c:214-223).  Replaces any previous tree of the scene. */
+int rt_scene_build_bvh(rt_scene* s, int heuristic);
+/* Fill a borrowed view (valid until the scene is changed or freed). */
+int rt_scene_view(const rt_scene* s, rt_scene_desc* out);
+void rt_scene_free(rt_scene* s);
+
+/* ------------------------------------------------------------------------------------
+ * Device context — replaces load_to_gpu / render_frame / load_from_gpu.
+ * ------------------------------------------------------------------------------------ */
+typedef struct rt_ctx rt_ctx;
+
+/* Camera with cam_init semantics (cpu/src/cam.c:5-9, cpu/src/main.c:105-106): fov is the
+ * full field-of-view angle in radians as passed to cam_init; rot is Euler Y->X->Z. */
+typedef struct rt_camera {
+    float pos[3];
+    float rot[3];
+    float fov;
+} rt_camera;
+
+enum {
+    RT_MODE_FAST = 0,   /* FMA + reciprocal arithmetic, tolerance-checked against the oracle */
+    RT_MODE_STRICT = 1  /* IEEE op-for-op restatement: bit-identical to oracle/rt_oracle.c */
+};
+
+enum { /* rt_render_params.aov_mask */
+    RT_AOV_RGB_F32 = 1,  /* clamped float colour, 3 floats/pixel (the reference's pixels[]) */
+    RT_AOV_TRI_ID = 2,   /* first-hit triangle index of sample 0, -1 = miss */
+    RT_AOV_DEPTH = 4,    /* first-hit t of sample 0 (FLT_MAX = miss) */
+    RT_AOV_WORK = 8      /* count inner-node visits and triangle tests (slower build of the kernel) */
+};
+
+enum { /* rt_render_params.gather */
+    RT_GATHER_PEER_STORE = 0, /* fused: every device stores finished pixels straight into device 0's frame */
+    RT_GATHER_PEER_COPY = 1   /* unfused: local frame, then packed tile copy device->device 0 + unpack */
+};
+
+typedef struct rt_render_params {
+    rt_camera cam;
+    int32_t   width, height;
+    int32_t   spp;          /* >= 1; sample 0 is the reference's pixel-corner ray (include/rt_sampling.h) */
+    uint32_t  seed;
+    int32_t   bounces;      /* BOUNCES, cpu/include/options.h:52 (4) */
+    int32_t   mode;         /* RT_MODE_* */
+    int32_t   aov_mask;     /* RT_AOV_* ; the 8-bit BGRA frame is always produced */
+    int32_t   gather;       /* RT_GATHER_* (only meaningful with > 1 device in the context) */
+    /* Image partition for one-process-per-GPU use: this context renders only the tiles of
+     * part `part_index` out of `part_count` (interleaved 16x8 tiles, see rt_tile_owner).
+     * part_count <= 1 renders the whole image (split over the context's own devices). */
+    int32_t   part_index, part_count;
+    /* tuning knobs (0 = library default) */
+    int32_t   block_threads;    /* threads per CTA */
+    int32_t   ctas_per_sm;      /* persistent CTAs per SM */
+    int32_t   refill_threshold; /* leave the traversal loop when fewer lanes than this are active */
+    int32_t   reserved[5];
+} rt_render_params;
+
+typedef struct rt_timing {
+    float    kernel_ms[RT_MAX_DEVICES]; /* render kernel, CUDA events on the launching stream */
+    float    gather_ms;                 /* frame assembly on device 0 (0 for fused peer stores) */
+    float    total_ms;                  /* first launch -> frame complete on device 0 (events) */
+    uint64_t rays_closest;              /* bvh_traverse calls (cpu/src/raytracer.c:113) */
+    uint64_t rays_shadow;               /* bvh_light_traverse calls (cpu/src/raytracer.c:74) */
+    uint64_t inner_visits;              /* RT_AOV_WORK only */
+    uint64_t tri_tests;                 /* RT_AOV_WORK only */
+    uint32_t launches;                  /* kernels launched by this call */
+    uint32_t n_devices;
+} rt_timing;
+
+void rt_render_params_default(rt_render_params* p); /* reference defaults: 1920x1080, camera of main.c:105-106 */
+
+/* load_to_gpu: flatten + compress the scene and upload it to every listed device.
+ * devices == NULL / ndev == 0 means device 0 only.  desc->bvh must be present. */
+int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** out);
+/* render_frame: blocking; renders into device-resident frame(s). */
+int rt_render(rt_ctx* ctx, const rt_render_params* params, rt_timing* timing_out);
+/* load_from_gpu: copy the last frame to host.  bgra: W*H*4 bytes, row 0 = top, bytes
+ * B,G,R,255 exactly as vec_to_bgra (cpu/src/bmp_writer.c:88-95).  The other outputs are
+ * optional (NULL) and require the matching RT_AOV_* bit in the last rt_render. */
+int rt_download(rt_ctx* ctx, uint8_t* bgra, float* rgb, int32_t* tri_id, float* depth_t);
+void rt_destroy(rt_ctx* ctx);
+/* Message of the last failure on this context (ctx == NULL: of the calling thread). */
+const char* rt_last_error(const rt_ctx* ctx);
+
+/* -------- one-process-per-GPU frame assembly (torch.distributed / NCCL plumbing) -------- */
+/* Tile geometry shared by the kernel, the pack/unpack kernels and the host. */
+#define RT_TILE_W 16
+#define RT_TILE_H 8
+/* owner part of tile (tx,ty): diagonal interleave */
+static inline int rt_tile_owner(int tx, int ty, int part_count) { return part_count > 1 ? (tx + ty) % part_count : 0; }
+/* Number of tiles part `part` owns in a width x height image. */
+int rt_part_tile_count(int width, int height, int part_index, int part_count);
+/* Device pointer (on the context's first device) of the packed BGRA tiles of the last
+ * render: rt_part_tile_count(...) * RT_TILE_W*RT_TILE_H*4 bytes, tiles in owner order. */
+int rt_packed_tiles(rt_ctx* ctx, void** dev_ptr, size_t* bytes);
+/* Scatter `part_count` packed buffers (concatenated, each `stride_bytes` long, device
+ * memory on the context's first device) into the context's BGRA frame. */
+int rt_unpack_tiles(rt_ctx* ctx, const void* dev_gathered, size_t stride_bytes, int part_count);
+/* CUDA IPC: export the BGRA frame of this context (64-byte handle) / make another
+ * process's frame the peer-store target of this context's renders. */
+int rt_frame_ipc_export(rt_ctx* ctx, int width, int height, void* handle64);
+int rt_frame_ipc_import(rt_ctx* ctx, const void* handle64, int width, int height);
+/* Raw device pointer of the BGRA frame (device 0 of the context). */
+int rt_frame_device_ptr(rt_ctx* ctx, void** dev_ptr, size_t* bytes);
+
+/* -------- image output (cpu/src/bmp_writer.c:177-211) -------- */
+/* 54-byte header, 32 bpp, bottom-up rows; input is the top-down BGRA of rt_download. */
+int rt_write_bmp(const char* path, const uint8_t* bgra_top_down, int width, int height);
+
+int rt_abi_version(void);
+/* number of visible CUDA devices (0 when there is none / no driver) */
+int rt_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

@@ -1,0 +1,611 @@
+/*
+ * rt_oracle.c — TEST INFRASTRUCTURE.  Plain-C, strict-IEEE restatement of the reference CPU
+ * renderer's hot path (deluf/parallel-ray-tracer, cpu/).  Nothing in the product links,
+ * loads or calls this file: only tests/, __graft_entry__.smoke() and bench.py's CPU arm do,
+ * and only as the checker.
+ *
+ * PARITY PINNING: this restatement is pinned against the reference itself, compiled
+ * unmodified into oracle/_ref/ref_cpu_* (oracle/Makefile, oracle/ref_harness.c):
+ *   - tests/test_oracle_vs_reference.py compares, per pixel, first-hit ID / t / colour of
+ *     both shipped scenes (and the reference's own synthetic soup) when oracle/_ref exists;
+ *   - tests/golden/ holds AOVs and BVH digests produced by that reference binary
+ *     (scripts/make_golden.py), compared on every run, with or without oracle/_ref.
+ * The reference is built with -ffast-math, this file with -fno-fast-math -ffp-contract=off,
+ * so agreement with the reference is "all but a handful of edge pixels" (the reference's
+ * own -O2 vs -O3 -ffast-math builds differ on 55 of 2 073 600 pixels),
+ * while agreement between this file and the CUDA kernel in RT_MODE_STRICT is bit-exact.
+ *
+ * Every function cites the reference lines it follows.  Arithmetic is written operation
+ * for operation in the reference's order; do not "simplify" expressions here.
+ *
+ * Build: oracle/Makefile target `oracle` (gcc -std=c11 -O2 -fno-fast-math -ffp-contract=off).
+ */
+#define _GNU_SOURCE
+#include <float.h>
+#include <math.h>
+#include <pthread.h>
+#include <stdatomic.h>
+#include <stdbool.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "rt_sampling.h"
+
+/* ---------------------------------------------------------------- vec (cpu/src/vec.c) */
+typedef struct { float x, y, z; } v3;
+
+static inline float v_dot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }           /* vec.c:4-6 */
+static inline float v_mag(v3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }          /* vec.c:15-17 */
+static inline v3 v_mul(v3 a, float s) { return (v3){a.x * s, a.y * s, a.z * s}; }             /* vec.c:23-25 */
+static inline v3 v_add(v3 a, v3 b) { return (v3){a.x + b.x, a.y + b.y, a.z + b.z}; }          /* vec.c:27-29 */
+static inline v3 v_sub(v3 a, v3 b) { return (v3){a.x - b.x, a.y - b.y, a.z - b.z}; }          /* vec.c:31-33 */
+static inline v3 v_div(v3 a, float s) { return (v3){a.x / s, a.y / s, a.z / s}; }             /* vec.c:35-37 */
+static inline v3 v_cross(v3 a, v3 b)                                                           /* vec.c:39-45 */
+{
+    return (v3){a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+static inline v3 v_normalize(v3 a) { return v_div(a, v_mag(a)); }                              /* vec.c:19-21 */
+
+/* ---------------------------------------------------------------- scene */
+typedef struct {
+    v3 c[3];          /* coords, cpu/include/triangle.h:9 */
+    float centroid[3];
+    v3 ks, kd, kr;
+    v3 norm[2];
+} tri_t;
+
+typedef struct { float min[3], max[3]; int32_t tr_len, idx; } node_t; /* cpu/include/bvh.h:9-23 */
+
+typedef struct { v3 pos, kl; } light_t; /* cpu/include/light.h:8-11 */
+
+typedef struct ro_scene {
+    tri_t* tris; uint32_t n_tris;
+    float* centroid_fm; /* centroids as the reference's -ffast-math binary computes them (see ro_build_bvh) */
+    light_t* lights; uint32_t n_lights;
+    v3 amb;
+    node_t* bvh; int32_t* tri_idx; int32_t bvh_len;
+} ro_scene;
+
+/* triangle_init, cpu/src/triangle.c:6-24 */
+static void tri_init(tri_t* t, v3 a, v3 b, v3 c, v3 ks, v3 kd, v3 kr)
+{
+    t->c[0] = a; t->c[1] = b; t->c[2] = c;
+    t->ks = ks; t->kd = kd; t->kr = kr;
+    v3 e1 = v_sub(b, a), e2 = v_sub(c, a);
+    t->norm[0] = v_normalize(v_cross(e1, e2));
+    t->norm[1] = v_normalize(v_cross(e2, e1));
+    t->centroid[0] = (a.x + b.x + c.x) / 3.0f;
+    t->centroid[1] = (a.y + b.y + c.y) / 3.0f;
+    t->centroid[2] = (a.z + b.z + c.z) / 3.0f;
+}
+
+ro_scene* ro_scene_create(const float* tri9, const uint32_t* mat_idx, uint32_t n_tris, const float* mats9,
+                          uint32_t n_mats, const float* lights6, uint32_t n_lights, const float* amb3)
+{
+    ro_scene* s = calloc(1, sizeof *s);
+    s->n_tris = n_tris;
+    s->tris = malloc(sizeof(tri_t) * (n_tris ? n_tris : 1));
+    for (uint32_t i = 0; i < n_tris; i++) {
+        const float* p = tri9 + 9 * (size_t)i;
+        uint32_t m = mat_idx ? mat_idx[i] : 0;
+        v3 ks = {0, 0, 0}, kd = {0, 0, 0}, kr = {0, 0, 0};
+        if (m < n_mats) {
+            const float* k = mats9 + 9 * (size_t)m;
+            ks = (v3){k[0], k[1], k[2]}; kd = (v3){k[3], k[4], k[5]}; kr = (v3){k[6], k[7], k[8]};
+        }
+        tri_init(&s->tris[i], (v3){p[0], p[1], p[2]}, (v3){p[3], p[4], p[5]}, (v3){p[6], p[7], p[8]}, ks, kd, kr);
+    }
+    s->n_lights = n_lights;
+    s->lights = malloc(sizeof(light_t) * (n_lights ? n_lights : 1));
+    for (uint32_t i = 0; i < n_lights; i++) {
+        const float* l = lights6 + 6 * (size_t)i;
+        s->lights[i].pos = (v3){l[0], l[1], l[2]};
+        s->lights[i].kl = (v3){l[3], l[4], l[5]};
+    }
+    s->amb = (v3){amb3[0], amb3[1], amb3[2]}; /* cpu/src/main.c:37 */
+    return s;
+}
+
+void ro_scene_free(ro_scene* s)
+{
+    if (!s) return;
+    free(s->tris); free(s->lights); free(s->bvh); free(s->tri_idx); free(s->centroid_fm); free(s);
+}
+
+/* ---------------------------------------------------------------- BVH build (cpu/src/bvh.c:22-267, 360-388) */
+#define BVH_MAX_ITER 32          /* cpu/include/options.h:64 */
+#define BVH_ELEMENT_THRESHOLD 2  /* cpu/include/options.h:58 */
+#define SAH_BIN_SIZE 32          /* cpu/include/options.h:61 */
+
+typedef struct { v3 min, max; } box_t;
+
+static inline float box_area(const box_t* b) { v3 s = v_sub(b->max, b->min); return v_dot(s, s); } /* bvh.c:43-46 (squared diagonal) */
+static inline void box_grow_pt(box_t* b, v3 p)                                                      /* bvh.c:61-64, vec.c:56-68 */
+{
+    b->min = (v3){fminf(b->min.x, p.x), fminf(b->min.y, p.y), fminf(b->min.z, p.z)};
+    b->max = (v3){fmaxf(b->max.x, p.x), fmaxf(b->max.y, p.y), fmaxf(b->max.z, p.z)};
+}
+static inline void box_grow_tr(box_t* b, const tri_t* t) { box_grow_pt(b, t->c[0]); box_grow_pt(b, t->c[1]); box_grow_pt(b, t->c[2]); } /* bvh.c:66-71 */
+
+static inline box_t node_box(const node_t* n) { return (box_t){{n->min[0], n->min[1], n->min[2]}, {n->max[0], n->max[1], n->max[2]}}; }
+static inline void node_set_box(node_t* n, const box_t* b)
+{
+    n->min[0] = b->min.x; n->min[1] = b->min.y; n->min[2] = b->min.z;
+    n->max[0] = b->max.x; n->max[1] = b->max.y; n->max[2] = b->max.z;
+}
+static inline float v_get(v3 v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+
+typedef struct { ro_scene* s; int heuristic; int refbin; } build_t;
+
+/* RO_BVH_REFBIN: the reference CPU program is built with -O3 -ffast-math -march=native
+ * (cpu/makefile:14).  gcc 13 on an FMA-capable x86-64 then evaluates four expressions of the
+ * heuristic-6 search differently from their IEEE reading (disassembly of bvh_split and
+ * triangle_init in oracle/_ref/ref_cpu_h6.*), which flips a few near-tied split decisions
+ * (about 2 % of the nodes of the shipped scenes):
+ *     centroid  = ((a + b) + c) * 0.33333334f            instead of (a + b + c) / 3.0f
+ *     split     = fmaf((float)i, size * 0.03125f, min)    instead of min + size * ((float)i / 32)
+ *     diag2     = fmaf(dz, dz, fmaf(dx, dx, dy * dy))     instead of dx*dx + dy*dy + dz*dz
+ *     score     = fmaf(cl, diag2_l, cr * diag2_r)         instead of cl*diag2_l + cr*diag2_r
+ * With this flag the restatement reproduces that binary's tree node for node; without it,
+ * the IEEE reading (which is also what the reference GPU program's host code computes,
+ * since nvcc does not pass fast-math to the host compiler). */
+#define RO_BVH_REFBIN 0x100
+
+static inline float box_area_fm(const box_t* b)
+{
+    v3 s = v_sub(b->max, b->min);
+    return fmaf(s.z, s.z, fmaf(s.x, s.x, s.y * s.y));
+}
+
+/* bvh_split, cpu/src/bvh.c:78-267 (heuristics 0, 1 and 6; 2/3 depend on libc rand() and an
+ * out-of-bounds axis, 4/5 on qsort tie order — SURVEY.md §C.1 — and are not restated). */
+static void split(build_t* B, int node_idx, int depth)
+{
+    ro_scene* s = B->s;
+    node_t* parent = &s->bvh[node_idx];
+    if ((size_t)s->bvh_len >= 2 * (size_t)s->n_tris) return;                          /* :80-83 */
+    if (depth == BVH_MAX_ITER || parent->tr_len <= BVH_ELEMENT_THRESHOLD) {           /* :84 */
+        if (!parent->tr_len) parent->idx = 0;                                         /* :85-86 */
+        return;
+    }
+    int child_idx = s->bvh_len;                                                       /* :98-99 */
+    s->bvh_len += 2;
+    node_t* left = &s->bvh[child_idx];
+    node_t* right = &s->bvh[child_idx + 1];
+    box_t lb = {{1e10f, 1e10f, 1e10f}, {-1e10f, -1e10f, -1e10f}}, rb = lb;           /* :104-108 */
+    left->idx = parent->idx;                                                          /* :103 */
+    right->idx = parent->idx;                                                         /* :106 */
+
+    box_t pb = node_box(parent);
+    int splitAxis = 0;
+    float splitPos = 0;
+    v3 center = v_mul(v_add(pb.min, pb.max), 0.5f);                                   /* :112, :38-41 */
+    v3 size = v_sub(pb.max, pb.min);                                                  /* :113 */
+
+    if (B->heuristic == 6) {                                                          /* :138-177 */
+        float best_score = FLT_MAX;
+        for (int axis = 0; axis < 3; axis++) {
+            for (int i = 0; i < SAH_BIN_SIZE; i++) {
+                box_t al, ar;
+                al.max = ar.max = (v3){FLT_MIN, FLT_MIN, FLT_MIN};                    /* :149 (positive tiny, sic) */
+                al.min = ar.min = (v3){FLT_MAX, FLT_MAX, FLT_MAX};                    /* :150 */
+                v3 sz = v_sub(pb.max, pb.min);                                        /* :156 */
+                float sp = v_get(pb.min, axis) + v_get(sz, axis) * ((float)i / SAH_BIN_SIZE); /* :157 */
+                if (B->refbin) sp = fmaf((float)i, v_get(sz, axis) * 0.03125f, v_get(pb.min, axis));
+                int cl = 0, cr = 0;
+                for (int j = parent->idx; j < parent->idx + parent->tr_len; j++) {    /* :161-168 */
+                    const tri_t* t = &s->tris[s->tri_idx[j]];
+                    float ce = B->refbin ? s->centroid_fm[3 * (size_t)s->tri_idx[j] + axis] : t->centroid[axis];
+                    bool inA = ce < sp;
+                    box_grow_tr(inA ? &al : &ar, t);
+                    if (inA) cl++; else cr++;
+                }
+                float score = cl * box_area(&al) + cr * box_area(&ar);                /* :169 */
+                if (B->refbin) score = fmaf((float)cl, box_area_fm(&al), (float)cr * box_area_fm(&ar));
+                if (score < best_score) { best_score = score; splitAxis = axis; splitPos = sp; } /* :170-174 */
+            }
+        }
+    } else if (B->heuristic == 0) {                                                   /* :214-217 */
+        splitAxis = 0;
+        splitPos = v_get(center, 0);
+    } else {                                                                          /* heuristic 1, :218-223 */
+        splitAxis = 0;
+        if (size.y > size.x) splitAxis = 1;
+        if (size.z > size.x && size.z > size.y) splitAxis = 2;
+        splitPos = v_get(center, splitAxis);
+    }
+
+    for (int i = parent->idx; i < parent->idx + parent->tr_len; i++) {                /* :244-259 */
+        int t_idx = s->tri_idx[i];
+        const tri_t* t = &s->tris[t_idx];
+        float ce = B->refbin ? s->centroid_fm[3 * (size_t)t_idx + splitAxis] : t->centroid[splitAxis];
+        bool inA = ce < splitPos;
+        if (inA) { box_grow_tr(&lb, t); left->tr_len += 1; }
+        else { box_grow_tr(&rb, t); right->tr_len += 1; }
+        if (inA) {
+            int swap = left->idx + left->tr_len - 1;
+            int tmp = s->tri_idx[i];
+            s->tri_idx[i] = s->tri_idx[swap];
+            s->tri_idx[swap] = tmp;
+            right->idx += 1;
+        }
+    }
+    node_set_box(left, &lb);
+    node_set_box(right, &rb);
+    parent->idx = child_idx;                                                          /* :262-263 */
+    parent->tr_len = 0;
+    split(B, child_idx, depth + 1);                                                   /* :265-266 */
+    split(B, child_idx + 1, depth + 1);
+}
+
+/* bvh_build, cpu/src/bvh.c:360-388 */
+int ro_build_bvh(ro_scene* s, int heuristic)
+{
+    if (!s || !s->n_tris) return -1;
+    int refbin = (heuristic & RO_BVH_REFBIN) != 0;
+    heuristic &= ~RO_BVH_REFBIN;
+    if (heuristic != 6 && heuristic != 0 && heuristic != 1) return -1;
+    if (refbin && !s->centroid_fm) {
+        s->centroid_fm = malloc(sizeof(float) * 3 * (size_t)s->n_tris);
+        for (uint32_t i = 0; i < s->n_tris; i++) {
+            const tri_t* t = &s->tris[i];
+            s->centroid_fm[3 * (size_t)i + 0] = ((t->c[0].x + t->c[1].x) + t->c[2].x) * 0.33333334f;
+            s->centroid_fm[3 * (size_t)i + 1] = ((t->c[0].y + t->c[1].y) + t->c[2].y) * 0.33333334f;
+            s->centroid_fm[3 * (size_t)i + 2] = ((t->c[0].z + t->c[1].z) + t->c[2].z) * 0.33333334f;
+        }
+    }
+    free(s->bvh); free(s->tri_idx);
+    s->tri_idx = malloc(sizeof(int32_t) * s->n_tris);
+    for (uint32_t i = 0; i < s->n_tris; i++) s->tri_idx[i] = (int32_t)i;
+    s->bvh = calloc(2 * (size_t)s->n_tris, sizeof(node_t));
+    s->bvh_len = 1;
+    s->bvh[0].tr_len = (int32_t)s->n_tris;
+    box_t rb = {{1e10f, 1e10f, 1e10f}, {-1e10f, -1e10f, -1e10f}};
+    for (uint32_t i = 0; i < s->n_tris; i++) box_grow_tr(&rb, &s->tris[i]);
+    node_set_box(&s->bvh[0], &rb);
+    build_t B = {s, heuristic, refbin};
+    split(&B, 0, 0);
+    return 0;
+}
+
+int ro_set_bvh(ro_scene* s, const void* nodes32, const int32_t* tri_idx, int32_t bvh_len)
+{
+    free(s->bvh); free(s->tri_idx);
+    s->bvh = malloc(sizeof(node_t) * (size_t)bvh_len);
+    memcpy(s->bvh, nodes32, sizeof(node_t) * (size_t)bvh_len);
+    s->tri_idx = malloc(sizeof(int32_t) * s->n_tris);
+    memcpy(s->tri_idx, tri_idx, sizeof(int32_t) * s->n_tris);
+    s->bvh_len = bvh_len;
+    return 0;
+}
+
+int32_t ro_bvh_len(const ro_scene* s) { return s->bvh_len; }
+const void* ro_bvh_nodes(const ro_scene* s) { return s->bvh; }
+const int32_t* ro_tri_idx(const ro_scene* s) { return s->tri_idx; }
+
+/* ---------------------------------------------------------------- intersection */
+static const float EPSILON = 1e-3; /* cpu/src/raytracer.c:19 */
+
+typedef struct { uint64_t closest, shadow, inner, tris, boxes; } counters_t;
+
+/* hit_triangle, cpu/src/raytracer.c:35-59 */
+static float hit_triangle(v3 origin, v3 dir, const tri_t* tr, int* norm_dir)
+{
+    v3 e1 = v_sub(tr->c[1], tr->c[0]);
+    v3 e2 = v_sub(tr->c[2], tr->c[0]);
+    v3 n = v_cross(e1, e2);
+    float det = -v_dot(dir, n);
+    *norm_dir = det < 0.0f;
+    float abs_det = fabsf(det);
+    if (abs_det < EPSILON) return FLT_MAX;
+    float invdet = 1.0f / det;
+    v3 ao = v_sub(origin, tr->c[0]);
+    v3 dao = v_cross(ao, dir);
+    float u = v_dot(e2, dao) * invdet;
+    float v = -v_dot(e1, dao) * invdet;
+    float t = v_dot(ao, n) * invdet;
+    if (t > EPSILON && u >= 0.0f && v >= 0.0f && (u + v) <= 1.0f) return t;
+    return FLT_MAX;
+}
+
+/* aabb_intersect, cpu/src/bvh.c:48-59 */
+static float aabb_intersect(const node_t* b, v3 o, v3 d)
+{
+    float tx1 = (b->min[0] - o.x) / d.x, tx2 = (b->max[0] - o.x) / d.x;
+    float tmin = fminf(tx1, tx2), tmax = fmaxf(tx1, tx2);
+    float ty1 = (b->min[1] - o.y) / d.y, ty2 = (b->max[1] - o.y) / d.y;
+    tmin = fmaxf(tmin, fminf(ty1, ty2)), tmax = fminf(tmax, fmaxf(ty1, ty2));
+    float tz1 = (b->min[2] - o.z) / d.z, tz2 = (b->max[2] - o.z) / d.z;
+    tmin = fmaxf(tmin, fminf(tz1, tz2)), tmax = fminf(tmax, fmaxf(tz1, tz2));
+    bool cond = tmax >= tmin && tmax > 0;
+    if (cond) return tmin;
+    return FLT_MAX;
+}
+
+/* bvh_traverse, cpu/src/bvh.c:317-358 */
+static void bvh_traverse(const ro_scene* s, v3 origin, v3 dir, int* norm_dir, float* t, int* t_idx, counters_t* c)
+{
+    int stack[64];
+    int sp = 0;
+    stack[sp++] = 0;
+    c->closest++;
+    while (sp) {
+        const node_t* node = &s->bvh[stack[--sp]];
+        if (node->tr_len) {
+            for (int i = node->idx; i < node->idx + node->tr_len; i++) {
+                int nt;
+                int it = s->tri_idx[i];
+                c->tris++;
+                float tt = hit_triangle(origin, dir, &s->tris[it], &nt);
+                if (tt < *t) { *t = tt; *norm_dir = nt; *t_idx = it; }
+            }
+        } else if (node->idx) {
+            int near_idx = node->idx, far_idx = node->idx + 1;
+            c->inner++; c->boxes += 2;
+            float near_t = aabb_intersect(&s->bvh[near_idx], origin, dir);
+            float far_t = aabb_intersect(&s->bvh[far_idx], origin, dir);
+            if (far_t < near_t) {
+                int ti = near_idx; float tf = near_t;
+                near_idx = far_idx; near_t = far_t; far_idx = ti; far_t = tf;
+            }
+            if (far_t < *t) stack[sp++] = far_idx;
+            if (near_t < *t) stack[sp++] = near_idx;
+        }
+    }
+}
+
+/* bvh_light_traverse, cpu/src/bvh.c:269-315 */
+static bool bvh_light_traverse(const ro_scene* s, v3 origin, v3 dir, float* t, float light_dist2, counters_t* c)
+{
+    int stack[64];
+    int sp = 0;
+    stack[sp++] = 0;
+    c->shadow++;
+    while (sp) {
+        const node_t* node = &s->bvh[stack[--sp]];
+        if (node->tr_len) {
+            for (int i = node->idx; i < node->idx + node->tr_len; i++) {
+                int nt;
+                int it = s->tri_idx[i];
+                c->tris++;
+                float tt = hit_triangle(origin, dir, &s->tris[it], &nt);
+                if (tt < *t) {
+                    *t = tt;
+                    v3 ds = v_mul(dir, *t);
+                    v3 inter = v_add(origin, ds);
+                    v3 omi = v_sub(origin, inter);
+                    if (light_dist2 > v_dot(omi, omi)) return false;
+                }
+            }
+        } else if (node->idx) {
+            int near_idx = node->idx, far_idx = node->idx + 1;
+            c->inner++; c->boxes += 2;
+            float near_t = aabb_intersect(&s->bvh[near_idx], origin, dir);
+            float far_t = aabb_intersect(&s->bvh[far_idx], origin, dir);
+            if (far_t < near_t) {
+                int ti = near_idx; float tf = near_t;
+                near_idx = far_idx; near_t = far_t; far_idx = ti; far_t = tf;
+            }
+            if (far_t < *t) stack[sp++] = far_idx;
+            if (near_t < *t) stack[sp++] = near_idx;
+        }
+    }
+    return true;
+}
+
+/* ---------------------------------------------------------------- shading (cpu/src/raytracer.c) */
+/* lambert_blinn, raytracer.c:21-33 */
+static v3 lambert_blinn(v3 ks, v3 kd, v3 n, v3 l, v3 v, float dot)
+{
+    v3 h = v_normalize(v_add(l, v));
+    float coeff = (float)fmax(0, v_dot(n, h));
+    v3 out;
+    out.x = kd.x * fmaxf(0, dot) + ks.x * coeff;
+    out.y = kd.y * fmaxf(0, dot) + ks.y * coeff;
+    out.z = kd.z * fmaxf(0, dot) + ks.z * coeff;
+    return out;
+}
+
+/* light_v, raytracer.c:62-99 (USE_BVH 1, USE_BVH_FAST_LIGHT 1) */
+static int light_v(const ro_scene* s, v3 origin, v3 dir, v3 n, v3 light, counters_t* c)
+{
+    v3 tmp = v_sub(origin, light);
+    v3 tmp2 = v_sub(light, origin);
+    float light_dist2 = v_dot(tmp, tmp);
+    if (v_dot(tmp2, n) < 0) return 0;
+    float t = FLT_MAX;
+    return bvh_light_traverse(s, origin, dir, &t, light_dist2, c);
+}
+
+/* raytrace, raytracer.c:101-176 */
+static v3 raytrace(const ro_scene* s, v3 origin, v3 dir, int iter, int bounces, counters_t* c)
+{
+    v3 col = {0, 0, 0};
+    if (iter == bounces) return col;
+    int index = -1;
+    float t = FLT_MAX;
+    int norm_dir = 0;
+    bvh_traverse(s, origin, dir, &norm_dir, &t, &index, c);
+    if (index == -1) {
+        col.x += s->amb.x; col.y += s->amb.y; col.z += s->amb.z;
+    } else {
+        v3 dir_scaled = v_mul(dir, t);
+        v3 inter = v_add(origin, dir_scaled);
+        const tri_t* tr = &s->tris[index];
+        v3 ks = tr->ks, kd = tr->kd, kr = tr->kr;
+        v3 n = tr->norm[norm_dir];
+        col.x += kd.x * s->amb.x; col.y += kd.y * s->amb.y; col.z += kd.z * s->amb.z;
+        dir = v_mul(dir, -1.0f);
+        for (uint32_t i = 0; i < s->n_lights; i++) {
+            v3 l = v_sub(s->lights[i].pos, inter);
+            float mag = v_mag(l);
+            l = v_div(l, mag);
+            mag *= mag;
+            float n_dot_l = v_dot(n, l);
+            v3 col_ray = lambert_blinn(ks, kd, n, l, dir, n_dot_l);
+            int V = light_v(s, inter, l, n, s->lights[i].pos, c);
+            col.x += V * s->lights[i].kl.x * col_ray.x / mag;
+            col.y += V * s->lights[i].kl.y * col_ray.y / mag;
+            col.z += V * s->lights[i].kl.z * col_ray.z / mag;
+        }
+        dir = v_mul(dir, -1);
+        v3 n_scaled = v_mul(n, 2 * fabsf(v_dot(dir, n)));
+        v3 r = v_normalize(v_add(dir, n_scaled));
+        if (v_mag(kr) > 0.0) {
+            v3 cr = raytrace(s, inter, r, iter + 1, bounces, c);
+            col.x += kr.x * cr.x; col.y += kr.y * cr.y; col.z += kr.z * cr.z;
+        }
+    }
+    return col;
+}
+
+/* ---------------------------------------------------------------- camera (cpu/src/cam.c) */
+typedef struct { v3 pos, rot; float fov; } cam_t;
+
+static void cam_rotX(const cam_t* c, v3* p) { v3 t = *p; p->y = t.y * cosf(c->rot.x) - t.z * sinf(c->rot.x); p->z = t.y * sinf(c->rot.x) + t.z * cosf(c->rot.x); }   /* cam.c:17-21 */
+static void cam_rotY(const cam_t* c, v3* p) { v3 t = *p; p->x = t.x * cosf(c->rot.y) + t.z * sinf(c->rot.y); p->z = -t.x * sinf(c->rot.y) + t.z * cosf(c->rot.y); }  /* cam.c:23-27 */
+static void cam_rotZ(const cam_t* c, v3* p) { v3 t = *p; p->x = t.x * cosf(c->rot.z) - t.y * sinf(c->rot.z); p->y = t.x * sinf(c->rot.z) + t.y * cosf(c->rot.z); }   /* cam.c:29-33 */
+static void cam_rotate(const cam_t* c, v3* p) { cam_rotY(c, p); cam_rotX(c, p); cam_rotZ(c, p); }                                                                         /* cam.c:11-15 */
+
+/* cam_init + cam_calculate_screen_coords + the increments of thread_render
+ * (cam.c:5-9, 35-48; cpu/src/main.c:241-250).  out = pos, ul, inc_x, inc_y (12 floats). */
+void ro_camera_basis(const float* pos3, const float* rot3, float fov, int width, int height, float* out12)
+{
+    cam_t cam;
+    cam.pos = (v3){pos3[0], pos3[1], pos3[2]};
+    cam.rot = (v3){rot3[0], rot3[1], rot3[2]};
+    cam.fov = 1.0 / tanf(fov / 2.0f);                       /* cam.c:8 (double divide, float store) */
+    float aspect = (float)width / height;                   /* main.c:243 */
+    v3 p[3] = {{-1 * aspect, cam.fov, +1}, {+1 * aspect, cam.fov, +1}, {-1 * aspect, cam.fov, -1}};
+    for (int i = 0; i < 3; i++) { cam_rotate(&cam, &p[i]); p[i] = v_add(p[i], cam.pos); }
+    v3 ul = p[0], ur = p[1], dl = p[2];
+    v3 inc_x = v_div(v_sub(ur, ul), width);                 /* main.c:247-248 */
+    v3 inc_y = v_div(v_sub(dl, ul), height);                /* main.c:249-250 */
+    float o[12] = {cam.pos.x, cam.pos.y, cam.pos.z, ul.x, ul.y, ul.z, inc_x.x, inc_x.y, inc_x.z, inc_y.x, inc_y.y, inc_y.z};
+    memcpy(out12, o, sizeof o);
+}
+
+/* ---------------------------------------------------------------- frame */
+typedef struct {
+    const ro_scene* s;
+    v3 pos, ul, inc_x, inc_y;
+    int w, h, spp, bounces;
+    uint32_t seed;
+    float* rgb; uint8_t* bgra; int32_t* id; float* depth;
+    atomic_int row;
+    pthread_mutex_t mu;
+    counters_t total;
+} job_t;
+
+/* render_pixel, cpu/src/main.c:228-234, with a sub-pixel offset (0,0 for the reference ray) */
+static v3 px_dir(const job_t* J, float fx, float fy)
+{
+    v3 dir = v_sub(J->ul, J->pos);
+    v3 px = v_mul(J->inc_x, fx);
+    v3 py = v_mul(J->inc_y, fy);
+    dir = v_add(dir, px);
+    dir = v_add(dir, py);
+    return dir;
+}
+
+static void* worker(void* arg)
+{
+    job_t* J = arg;
+    counters_t c = {0, 0, 0, 0, 0};
+    for (;;) {
+        int y = atomic_fetch_add(&J->row, 1); /* cpu/src/main.c:253 with TILE_SIZE == WIDTH */
+        if (y >= J->h) break;
+        for (int x = 0; x < J->w; x++) {
+            size_t idx = (size_t)y * J->w + x;
+            v3 sum = {0, 0, 0};
+            for (int sm = 0; sm < J->spp; sm++) {
+                float jx, jy;
+                rt_sample_offset((uint32_t)x, (uint32_t)y, (uint32_t)sm, J->seed, &jx, &jy);
+                v3 dir = px_dir(J, (float)x + jx, (float)y + jy);
+                if (sm == 0 && (J->id || J->depth)) {
+                    /* first-hit AOVs: one extra closest-hit query, not counted as a ray */
+                    counters_t scratch = {0, 0, 0, 0, 0};
+                    int nd = 0, id = -1; float t = FLT_MAX;
+                    bvh_traverse(J->s, J->pos, dir, &nd, &t, &id, &scratch);
+                    if (J->id) J->id[idx] = id;
+                    if (J->depth) J->depth[idx] = t;
+                }
+                v3 col = raytrace(J->s, J->pos, dir, 0, J->bounces, &c);
+                if (J->spp == 1) sum = col; else sum = v_add(sum, col);
+            }
+            if (J->spp > 1) sum = v_div(sum, (float)J->spp);
+            /* vec_constrain, cpu/src/vec.c:47-54 */
+            sum.x = fminf(fmaxf(sum.x, 0.0f), 1.0f);
+            sum.y = fminf(fmaxf(sum.y, 0.0f), 1.0f);
+            sum.z = fminf(fmaxf(sum.z, 0.0f), 1.0f);
+            if (J->rgb) { J->rgb[3 * idx] = sum.x; J->rgb[3 * idx + 1] = sum.y; J->rgb[3 * idx + 2] = sum.z; }
+            if (J->bgra) { /* vec_to_bgra, cpu/src/bmp_writer.c:88-95 */
+                J->bgra[4 * idx + 0] = (uint8_t)(sum.z * 255.0f);
+                J->bgra[4 * idx + 1] = (uint8_t)(sum.y * 255.0f);
+                J->bgra[4 * idx + 2] = (uint8_t)(sum.x * 255.0f);
+                J->bgra[4 * idx + 3] = 255;
+            }
+        }
+    }
+    pthread_mutex_lock(&J->mu);
+    J->total.closest += c.closest; J->total.shadow += c.shadow;
+    J->total.inner += c.inner; J->total.tris += c.tris; J->total.boxes += c.boxes;
+    pthread_mutex_unlock(&J->mu);
+    return NULL;
+}
+
+/* render_frame, cpu/src/main.c:214-226.  Any output pointer may be NULL.
+ * counters5 (optional) = closest rays, shadow rays, inner-node visits, triangle tests, box tests. */
+int ro_render(const ro_scene* s, const float* pos3, const float* rot3, float fov, int width, int height, int spp,
+              uint32_t seed, int bounces, int threads, float* rgb, uint8_t* bgra, int32_t* id, float* depth,
+              uint64_t* counters5)
+{
+    if (!s || !s->bvh || width < 1 || height < 1 || spp < 1 || threads < 1) return -1;
+    float b[12];
+    ro_camera_basis(pos3, rot3, fov, width, height, b);
+    job_t J;
+    memset(&J, 0, sizeof J);
+    J.s = s;
+    J.pos = (v3){b[0], b[1], b[2]}; J.ul = (v3){b[3], b[4], b[5]};
+    J.inc_x = (v3){b[6], b[7], b[8]}; J.inc_y = (v3){b[9], b[10], b[11]};
+    J.w = width; J.h = height; J.spp = spp; J.bounces = bounces; J.seed = seed;
+    J.rgb = rgb; J.bgra = bgra; J.id = id; J.depth = depth;
+    atomic_init(&J.row, 0);
+    pthread_mutex_init(&J.mu, NULL);
+    pthread_t* th = malloc(sizeof(pthread_t) * threads);
+    for (int i = 0; i < threads; i++) pthread_create(&th[i], NULL, worker, &J);
+    for (int i = 0; i < threads; i++) pthread_join(th[i], NULL);
+    free(th);
+    if (counters5) {
+        counters5[0] = J.total.closest; counters5[1] = J.total.shadow; counters5[2] = J.total.inner;
+        counters5[3] = J.total.tris; counters5[4] = J.total.boxes;
+    }
+    return 0;
+}
+
+/* ---------------------------------------------------------------- unit-level entry points for tests */
+float ro_hit_triangle(const float* o3, const float* d3, const float* tri9, int* norm_dir)
+{
+    tri_t t;
+    v3 z = {0, 0, 0};
+    tri_init(&t, (v3){tri9[0], tri9[1], tri9[2]}, (v3){tri9[3], tri9[4], tri9[5]}, (v3){tri9[6], tri9[7], tri9[8]}, z, z, z);
+    return hit_triangle((v3){o3[0], o3[1], o3[2]}, (v3){d3[0], d3[1], d3[2]}, &t, norm_dir);
+}
+
+float ro_aabb_intersect(const float* min3, const float* max3, const float* o3, const float* d3)
+{
+    node_t n;
+    memcpy(n.min, min3, 12); memcpy(n.max, max3, 12);
+    return aabb_intersect(&n, (v3){o3[0], o3[1], o3[2]}, (v3){d3[0], d3[1], d3[2]});
+}
+
+/* one ray: returns first-hit index (or -1), *t_out, *norm_dir_out */
+int ro_trace_closest(const ro_scene* s, const float* o3, const float* d3, float* t_out, int* norm_dir_out)
+{
+    counters_t c = {0, 0, 0, 0, 0};
+    int nd = 0, id = -1; float t = FLT_MAX;
+    bvh_traverse(s, (v3){o3[0], o3[1], o3[2]}, (v3){d3[0], d3[1], d3[2]}, &nd, &t, &id, &c);
+    *t_out = t; *norm_dir_out = nd;
+    return id;
+}
