@@ -97,7 +97,14 @@ int rt_scene_instance_grid(const rt_scene* base, uint32_t nx, uint32_t ny, uint3
                            const float pitch[3], uint32_t light_every, rt_scene** out);
 /* Host BVH build reproducing the reference tree node for node.  heuristic: 6 (binned
  * squared-diagonal "SAH", 32 bins; gpu/include/options.cuh:50), 0 or 1 (spatial median,
- * cpu/src/bvh.c:214-223).  Replaces any previous tree of the scene. */
+ * cpu/src/bvh.c:214-223).  Replaces any previous tree of the scene.
+ * Arithmetic: by default the IEEE reading of the reference source — which is what the
+ * reference GPU program's host code computes (nvcc passes no fast-math to the host compiler).
+ * OR-ing RT_BVH_REFBIN selects the four contracted expressions gcc 13 emits for the reference
+ * CPU program under its makefile flags (-O3 -ffast-math -march=native), reproducing THAT
+ * binary's tree node for node (it differs from the IEEE tree in ~2 % of the nodes; the image
+ * does not depend on which is used).  See csrc/bvh_build.cpp. */
+#define RT_BVH_REFBIN 0x100
 int rt_scene_build_bvh(rt_scene* s, int heuristic);
 /* Fill a borrowed view (valid until the scene is changed or freed). */
 int rt_scene_view(const rt_scene* s, rt_scene_desc* out);
@@ -185,7 +192,12 @@ const char* rt_last_error(const rt_ctx* ctx);
 #define RT_TILE_W 16
 #define RT_TILE_H 8
 /* owner part of tile (tx,ty): diagonal interleave */
-static inline int rt_tile_owner(int tx, int ty, int part_count) { return part_count > 1 ? (tx + ty) % part_count : 0; }
+#if defined(__CUDACC__)
+#define RT_INLINE_HD static inline __host__ __device__
+#else
+#define RT_INLINE_HD static inline
+#endif
+RT_INLINE_HD int rt_tile_owner(int tx, int ty, int part_count) { return part_count > 1 ? (tx + ty) % part_count : 0; }
 /* Number of tiles part `part` owns in a width x height image. */
 int rt_part_tile_count(int width, int height, int part_index, int part_count);
 /* Device pointer (on the context's first device) of the packed BGRA tiles of the last

@@ -258,7 +258,9 @@ int ro_build_bvh(ro_scene* s, int heuristic)
     free(s->bvh); free(s->tri_idx);
     s->tri_idx = malloc(sizeof(int32_t) * s->n_tris);
     for (uint32_t i = 0; i < s->n_tris; i++) s->tri_idx[i] = (int32_t)i;
-    s->bvh = calloc(2 * (size_t)s->n_tris, sizeof(node_t));
+    /* the reference allocates 2N nodes (bvh.c:370) but its guard (bvh.c:80) lets a split start at
+     * bvh_len == 2N-1 and write node 2N (possible with empty children, heuristics 0/1): two spare nodes */
+    s->bvh = calloc(2 * (size_t)s->n_tris + 2, sizeof(node_t));
     s->bvh_len = 1;
     s->bvh[0].tr_len = (int32_t)s->n_tris;
     box_t rb = {{1e10f, 1e10f, 1e10f}, {-1e10f, -1e10f, -1e10f}};

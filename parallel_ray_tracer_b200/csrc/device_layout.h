@@ -1,0 +1,68 @@
+// device_layout.h — the scene as it lives in HBM, and the per-frame kernel arguments.
+//
+// The reference GPU program keeps AoS triangles (48 B), split normals (32 B), a 24 B node with
+// FP16 boxes and walks nodes one at a time (gpu/src/gpu.cu:129-201, gpu/src/bvh.cu:342-392).
+// This layout is different by design:
+//
+//   nodes   one 64-byte record per INNER node holding BOTH child boxes in FP32 and both child
+//           references, so an inner visit is one 64 B fetch (4 x LDG.128) instead of the
+//           reference's pop fetch + two child fetches:
+//             q0 = (L.min.x, L.min.y, L.min.z, L.max.x)
+//             q1 = (L.max.y, L.max.z, R.min.x, R.min.y)
+//             q2 = (R.min.z, R.max.x, R.max.y, R.max.z)
+//             q3 = (left_ref, right_ref, 0, 0) as int bits
+//           L/R are the reference's children (child, child+1; cpu/include/bvh.h:19-22) so the
+//           reference's left-first tie rule (cpu/src/bvh.c:344) is preserved.
+//   refs    ref >= 0            : inner node index (into `nodes`)
+//           ref == RT_REF_NONE  : empty leaf / nothing (never pushed)
+//           otherwise (ref < 0) : leaf, ~ref = (first_slot << 4) | min(count, 15); count == 15
+//                                 means "look the count up in leaf_cnt[first_slot]"
+//   tris    48 bytes per LEAF-ORDER slot j (slot j holds triangle tri_idx[j], so a leaf's
+//           triangles are contiguous): q0 = (v0.xyz, e1.x) q1 = (e1.yz, e2.xy) q2 = (e2.z, n.xyz)
+//           with e1 = v1-v0, e2 = v2-v0, n = e1 x e2 computed in IEEE FP32 on the host in the
+//           reference's operation order (cpu/src/raytracer.c:36-38) — bit-identical to
+//           computing them per test, and never normalised.
+//   tri_orig[j]   original triangle index (the first-hit ID space)
+//   shade[orig]   (unit normal norm[0].xyz, material index as int bits); norm[1] == -norm[0]
+//   mats    3 x float4 per material: (ks, 0) (kd, 0) (kr, |kr| > 0 ? 1 : 0)
+//   lights  2 x float4 per light: (pos, 0) (kl, 0)
+#pragma once
+#include <stdint.h>
+#include "rt_b200.h"
+
+#define RT_TILE_PIXELS (RT_TILE_W * RT_TILE_H)
+
+#define RT_REF_NONE ((int)0x80000000)
+#define RT_LEAF_CNT_ESC 15
+#define RT_STACK_ENTRIES 36   /* reference depth cap 32 (cpu/include/options.h:64) -> at most 33 live entries */
+#define RT_MAX_BOUNCES 8
+
+struct RtDeviceScene {
+    const float4* nodes;
+    const float4* tris;
+    const int*    tri_orig;
+    const float4* shade;
+    const float4* mats;
+    const float4* lights;
+    const int*    leaf_cnt;
+    int   n_lights;
+    float amb[3];
+};
+
+struct RtFrameArgs {
+    // camera basis exactly as thread_render derives it (cpu/src/main.c:241-250)
+    float pos[3], ul[3], inc_x[3], inc_y[3];
+    int   width, height, spp, bounces;
+    unsigned seed;
+    int   tiles_x;                 // tiles per image row
+    const unsigned* tile_list;     // tiles this device renders (tile id = ty * tiles_x + tx)
+    int   n_tiles;
+    unsigned* tile_counter;        // persistent-CTA work counter (device-local)
+    int   refill_threshold;
+    // outputs (bgra may be a peer-mapped pointer into device 0's frame)
+    uchar4* bgra;
+    float*  rgb;                   // optional
+    int*    tri_id;                // optional
+    float*  depth;                 // optional
+    unsigned long long* stats;     // [0] closest rays [1] shadow rays [2] inner visits [3] triangle tests
+};

@@ -1,0 +1,159 @@
+// flatten.cpp — reference host layout (rt_scene_desc) -> the HBM layout of device_layout.h.
+// Runs once per rt_create (the reference's load_to_gpu marshalling, gpu/src/gpu.cu:129-201).
+// All derived quantities (edges, face normal, unit normal, |kr| > 0) are computed here in IEEE
+// FP32 in the reference's operation order, so the strict kernel sees the bits the oracle computes.
+// Must be compiled with -ffp-contract=off.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "flatten.h"
+#include "host_scene.h"
+
+namespace rt {
+
+static inline void sub3(const float* a, const float* b, float* o) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
+static inline void cross3(const float* a, const float* b, float* o) // vec_cross, cpu/src/vec.c:39-45
+{
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
+{
+    if (!d.n_tris || !d.tri_coords) { err = "scene has no triangles"; return RT_ERR_INVALID; }
+    if (!d.bvh || !d.tri_idx || !d.bvh_len) { err = "scene has no BVH (call rt_scene_build_bvh or supply bvh/tri_idx)"; return RT_ERR_INVALID; }
+    if (d.n_tris >= (1u << 27)) { err = "more than 2^27 triangles"; return RT_ERR_INVALID; }
+    const uint32_t n = d.n_tris, nb = d.bvh_len;
+    const uint32_t n_mats = d.n_mats ? d.n_mats : 1;
+
+    for (uint32_t j = 0; j < n; j++)
+        if (d.tri_idx[j] < 0 || (uint32_t)d.tri_idx[j] >= n) { err = "tri_idx entry out of range"; return RT_ERR_INVALID; }
+
+    // ---- triangles in leaf order ----
+    out.tris.resize(12 * (size_t)n);
+    out.tri_orig.resize(n);
+    out.shade.resize(4 * (size_t)n);
+    for (uint32_t j = 0; j < n; j++) {
+        const uint32_t orig = (uint32_t)d.tri_idx[j];
+        const float* c = d.tri_coords + 9 * (size_t)orig;
+        float e1[3], e2[3], nn[3];
+        sub3(c + 3, c, e1);  // raytracer.c:36
+        sub3(c + 6, c, e2);  // raytracer.c:37
+        cross3(e1, e2, nn);  // raytracer.c:38
+        float* q = &out.tris[12 * (size_t)j];
+        q[0] = c[0]; q[1] = c[1]; q[2] = c[2]; q[3] = e1[0];
+        q[4] = e1[1]; q[5] = e1[2]; q[6] = e2[0]; q[7] = e2[1];
+        q[8] = e2[2]; q[9] = nn[0]; q[10] = nn[1]; q[11] = nn[2];
+        out.tri_orig[j] = (int32_t)orig;
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        const float* c = d.tri_coords + 9 * (size_t)i;
+        float e1[3], e2[3], nn[3];
+        sub3(c + 3, c, e1);
+        sub3(c + 6, c, e2);
+        cross3(e1, e2, nn);                                                  // triangle.c:14-17
+        const float mag = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]); // vec_mag
+        float* s = &out.shade[4 * (size_t)i];
+        s[0] = nn[0] / mag; s[1] = nn[1] / mag; s[2] = nn[2] / mag;          // vec_normalize
+        uint32_t m = d.tri_mat ? d.tri_mat[i] : 0;
+        if (m >= n_mats) { err = "material index out of range"; return RT_ERR_INVALID; }
+        std::memcpy(&s[3], &m, 4);
+    }
+
+    // ---- materials / lights ----
+    out.mats.assign(12 * (size_t)n_mats, 0.0f);
+    for (uint32_t m = 0; m < d.n_mats; m++) {
+        const float* k = d.materials + 9 * (size_t)m;
+        float* q = &out.mats[12 * (size_t)m];
+        q[0] = k[0]; q[1] = k[1]; q[2] = k[2];
+        q[4] = k[3]; q[5] = k[4]; q[6] = k[5];
+        q[8] = k[6]; q[9] = k[7]; q[10] = k[8];
+        const float kr_mag = std::sqrt(k[6] * k[6] + k[7] * k[7] + k[8] * k[8]);
+        q[11] = (kr_mag > 0.0) ? 1.0f : 0.0f; // vec_mag(&kr) > 0.0, raytracer.c:168
+    }
+    out.lights.assign(8 * (size_t)(d.n_lights ? d.n_lights : 1), 0.0f);
+    for (uint32_t l = 0; l < d.n_lights; l++) {
+        const float* s = d.lights + 6 * (size_t)l;
+        float* q = &out.lights[8 * (size_t)l];
+        q[0] = s[0]; q[1] = s[1]; q[2] = s[2];
+        q[4] = s[3]; q[5] = s[4]; q[6] = s[5];
+    }
+    out.n_lights = d.n_lights;
+    std::memcpy(out.ambient, d.ambient, 12);
+
+    // ---- nodes: one record per inner node, DFS pre-order ----
+    auto is_inner = [&](const rt_bvh_node& b) { return b.tr_len == 0 && b.idx != 0; };
+    auto leaf_ref = [&](const rt_bvh_node& b, int32_t& ref) -> bool {
+        if (b.tr_len <= 0) { ref = RT_REF_NONE_HOST; return true; } // empty leaf: never pushed
+        if (b.idx < 0 || (uint64_t)b.idx + (uint64_t)b.tr_len > n) return false;
+        const int cnt = b.tr_len >= RT_LEAF_CNT_ESC_HOST ? RT_LEAF_CNT_ESC_HOST : b.tr_len;
+        if (b.tr_len >= RT_LEAF_CNT_ESC_HOST) {
+            if (out.leaf_cnt.empty()) out.leaf_cnt.assign(n, 0);
+            out.leaf_cnt[b.idx] = b.tr_len;
+        }
+        ref = ~((b.idx << 4) | cnt);
+        return true;
+    };
+
+    // pass 1: number the inner nodes (explicit stack; guards against cycles and bad indices)
+    std::vector<int32_t> inner_of(nb, -1);
+    std::vector<uint32_t> order; // reference node index of inner k
+    struct Item { uint32_t node; int depth; };
+    std::vector<Item> st;
+    int max_depth = 0;
+    if (is_inner(d.bvh[0])) st.push_back({0, 0});
+    while (!st.empty()) {
+        Item it = st.back();
+        st.pop_back();
+        const rt_bvh_node& b = d.bvh[it.node];
+        if (inner_of[it.node] >= 0) { err = "BVH is not a tree (node reached twice)"; return RT_ERR_INVALID; }
+        inner_of[it.node] = (int32_t)order.size();
+        order.push_back(it.node);
+        if (it.depth > max_depth) max_depth = it.depth;
+        if (b.idx < 1 || (uint64_t)b.idx + 1 >= nb) {
+            err = "BVH child index out of range";
+            return RT_ERR_INVALID;
+        }
+        // right first so that the left subtree is numbered first (pre-order)
+        if (is_inner(d.bvh[b.idx + 1])) st.push_back({(uint32_t)b.idx + 1, it.depth + 1});
+        if (is_inner(d.bvh[b.idx])) st.push_back({(uint32_t)b.idx, it.depth + 1});
+    }
+    // live stack entries never exceed (inner depth + 2)
+    if (max_depth + 3 > RT_STACK_ENTRIES_HOST) { err = "BVH deeper than the traversal stack (" + std::to_string(max_depth) + ")"; return RT_ERR_INVALID; }
+    out.max_depth = max_depth;
+
+    const size_t n_inner = order.empty() ? 1 : order.size();
+    out.nodes.assign(16 * n_inner, 0.0f);
+    auto put_child = [&](float* q, int which, const rt_bvh_node& c, int32_t ref) {
+        float mn[3], mx[3];
+        if (ref == RT_REF_NONE_HOST) { for (int a = 0; a < 3; a++) { mn[a] = 1e30f; mx[a] = -1e30f; } } // never hit
+        else { std::memcpy(mn, c.min, 12); std::memcpy(mx, c.max, 12); }
+        if (which == 0) { q[0] = mn[0]; q[1] = mn[1]; q[2] = mn[2]; q[3] = mx[0]; q[4] = mx[1]; q[5] = mx[2]; }
+        else { q[6] = mn[0]; q[7] = mn[1]; q[8] = mn[2]; q[9] = mx[0]; q[10] = mx[1]; q[11] = mx[2]; }
+        std::memcpy(&q[12 + which], &ref, 4);
+    };
+    if (order.empty()) {
+        // the root itself is a leaf (<= 2 triangles): synthetic inner node, left = root, right = none
+        int32_t ref;
+        if (!leaf_ref(d.bvh[0], ref)) { err = "BVH leaf range out of bounds"; return RT_ERR_INVALID; }
+        put_child(out.nodes.data(), 0, d.bvh[0], ref);
+        put_child(out.nodes.data(), 1, d.bvh[0], RT_REF_NONE_HOST);
+    }
+    for (size_t k = 0; k < order.size(); k++) {
+        const rt_bvh_node& b = d.bvh[order[k]];
+        float* q = &out.nodes[16 * k];
+        for (int w = 0; w < 2; w++) {
+            const rt_bvh_node& c = d.bvh[b.idx + w];
+            int32_t ref;
+            if (is_inner(c)) ref = inner_of[b.idx + w];
+            else if (!leaf_ref(c, ref)) { err = "BVH leaf range out of bounds"; return RT_ERR_INVALID; }
+            put_child(q, w, c, ref);
+        }
+    }
+    return RT_OK;
+}
+
+} // namespace rt

@@ -1,0 +1,17 @@
+// render_launch.h — host-visible launch interface of the two kernel builds.
+#pragma once
+#include <cuda_runtime.h>
+#include "device_layout.h"
+
+struct RtLaunchCfg {
+    int block_threads;  // 128 (default) or 64
+    int min_ctas;       // __launch_bounds__ second argument: caps registers/thread
+    bool work_counters; // RT_AOV_WORK build (counts inner visits and triangle tests)
+    int grid;           // number of persistent CTAs
+};
+
+cudaError_t rt_launch_fast(const RtDeviceScene& sc, const RtFrameArgs& fa, const RtLaunchCfg& cfg, cudaStream_t st);
+cudaError_t rt_launch_strict(const RtDeviceScene& sc, const RtFrameArgs& fa, const RtLaunchCfg& cfg, cudaStream_t st);
+// resident CTAs per SM and registers/thread of the instantiation cfg selects
+cudaError_t rt_occupancy_fast(const RtLaunchCfg& cfg, int* ctas_per_sm, int* regs);
+cudaError_t rt_occupancy_strict(const RtLaunchCfg& cfg, int* ctas_per_sm, int* regs);

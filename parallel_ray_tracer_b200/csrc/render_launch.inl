@@ -1,0 +1,48 @@
+// render_launch.inl — instantiation table; included inside render_{fast,strict}.cu.
+#include "render_launch.h"
+
+namespace RT_KERNEL_NS {
+
+typedef void (*kernel_fn)(const RtDeviceScene, const RtFrameArgs);
+
+template <bool WORK>
+static kernel_fn pick(int block, int minb)
+{
+    if (block == 64) {
+        if (minb >= 16) return render_kernel<64, 16, WORK>;
+        if (minb >= 12) return render_kernel<64, 12, WORK>;
+        return render_kernel<64, 8, WORK>;
+    }
+    if (minb >= 8) return render_kernel<128, 8, WORK>;
+    if (minb >= 6) return render_kernel<128, 6, WORK>;
+    if (minb >= 5) return render_kernel<128, 5, WORK>;
+    if (minb >= 4) return render_kernel<128, 4, WORK>;
+    if (minb >= 3) return render_kernel<128, 3, WORK>;
+    return render_kernel<128, 2, WORK>;
+}
+
+static kernel_fn pick(const RtLaunchCfg& c)
+{
+    return c.work_counters ? pick<true>(c.block_threads, c.min_ctas) : pick<false>(c.block_threads, c.min_ctas);
+}
+
+static cudaError_t launch(const RtDeviceScene& sc, const RtFrameArgs& fa, const RtLaunchCfg& cfg, cudaStream_t st)
+{
+    kernel_fn k = pick(cfg);
+    const int block = cfg.block_threads == 64 ? 64 : 128;
+    k<<<cfg.grid, block, 0, st>>>(sc, fa);
+    return cudaGetLastError();
+}
+
+static cudaError_t occupancy(const RtLaunchCfg& cfg, int* ctas_per_sm, int* regs)
+{
+    kernel_fn k = pick(cfg);
+    const int block = cfg.block_threads == 64 ? 64 : 128;
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, k);
+    if (e != cudaSuccess) return e;
+    if (regs) *regs = a.numRegs;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k, block, 0);
+}
+
+} // namespace RT_KERNEL_NS

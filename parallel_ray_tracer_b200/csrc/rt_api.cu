@@ -1,0 +1,600 @@
+// rt_api.cu — the C-ABI device context (include/rt_b200.h): rt_create / rt_render / rt_download /
+// rt_destroy and the frame-assembly helpers.  Host side of the reference GPU program's
+// load_to_gpu / render_frame / load_from_gpu (gpu/src/gpu.cu:98-228), made re-entrant,
+// error-checked (the reference checks one call, gpu.cu:121-124) and multi-device.
+//
+// Device work launched from here: the render kernel (render_fast.cu / render_strict.cu) and three
+// small frame kernels below (fill, pack, unpack).  There is no CPU rendering path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "camera.h"
+#include "device_layout.h"
+#include "flatten.h"
+#include "host_scene.h"
+#include "render_launch.h"
+
+namespace {
+
+struct Dev {
+    int id = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    // scene (replicated per device)
+    float4 *nodes = nullptr, *tris = nullptr, *shade = nullptr, *mats = nullptr, *lights = nullptr;
+    int *tri_orig = nullptr, *leaf_cnt = nullptr;
+    // per-frame control block: [0..3] stats (u64), then the tile counter
+    unsigned long long* ctrl = nullptr;
+    unsigned long long* ctrl_host = nullptr; // pinned
+    // tile list of this device for the current (w, h, parts)
+    unsigned* tile_list = nullptr;
+    int n_tiles = 0;
+    size_t tile_cap = 0;
+    // frame storage (device 0 owns the assembled frame; others only in PEER_COPY mode)
+    uchar4* bgra = nullptr;
+    size_t bgra_px = 0;
+    uchar4* packed = nullptr; // packed tiles (gather paths)
+    size_t packed_px = 0;
+    float* rgb = nullptr;
+    int* tri_id = nullptr;
+    float* depth = nullptr;
+    size_t aov_px[3] = {0, 0, 0};
+    bool peer_to_0 = false;
+};
+
+} // namespace
+
+struct rt_ctx {
+    std::vector<Dev> devs;
+    RtDeviceScene scene_host_view{}; // n_lights / amb only; pointers are per device
+    std::string err;
+    // state of the last render
+    int width = 0, height = 0, aov_mask = 0;
+    bool rendered = false;
+    int part_index = 0, part_count = 1;
+    // tile-list cache key
+    int tl_w = 0, tl_h = 0, tl_parts = 0, tl_index = -1;
+    // device 0 helpers for unpack
+    unsigned* local_index = nullptr; // per tile: index inside its owner's packed buffer
+    size_t local_index_cap = 0;
+    int li_w = 0, li_h = 0, li_parts = 0;
+    uchar4* gather_buf = nullptr; // in-process PEER_COPY landing zone on device 0
+    size_t gather_px = 0;
+    // imported frame of another process (CUDA IPC)
+    uchar4* ipc_frame = nullptr;
+    int ipc_w = 0, ipc_h = 0;
+    size_t scene_bytes = 0;
+};
+
+namespace {
+
+#define CK(ctx, call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess) {                                                                          \
+            (ctx)->err = std::string(#call) + " failed: " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                         std::to_string(__LINE__) + ")";                                                   \
+            rt::set_error((ctx)->err);                                                                     \
+            return RT_ERR_CUDA;                                                                            \
+        }                                                                                                  \
+    } while (0)
+
+int fail(rt_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg;
+    rt::set_error(msg);
+    return code;
+}
+
+template <class T>
+cudaError_t upload(T** dst, const void* src, size_t bytes, cudaStream_t st)
+{
+    if (!bytes) { *dst = nullptr; return cudaSuccess; }
+    cudaError_t e = cudaMalloc((void**)dst, bytes);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, st);
+}
+
+// ------------------------------------------------------------------ frame kernels
+__global__ void fill_bgra_kernel(uchar4* dst, size_t n, uchar4 v)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+
+// one CTA of RT_TILE_PIXELS threads per owned tile: frame -> packed (tile-major, row-major inside)
+__global__ void pack_tiles_kernel(const uchar4* __restrict__ frame, uchar4* __restrict__ packed,
+                                  const unsigned* __restrict__ tile_list, int n_tiles, int tiles_x, int width, int height)
+{
+    const int i = blockIdx.x;
+    if (i >= n_tiles) return;
+    const unsigned t = tile_list[i];
+    const int x = (int)(t % (unsigned)tiles_x) * RT_TILE_W + (threadIdx.x % RT_TILE_W);
+    const int y = (int)(t / (unsigned)tiles_x) * RT_TILE_H + (threadIdx.x / RT_TILE_W);
+    uchar4 v = make_uchar4(0, 0, 0, 0);
+    if (x < width && y < height) v = frame[(size_t)y * width + x];
+    packed[(size_t)i * RT_TILE_PIXELS + threadIdx.x] = v;
+}
+
+// one thread per pixel: gathered packed buffers -> frame
+__global__ void unpack_tiles_kernel(uchar4* __restrict__ frame, const uchar4* __restrict__ gathered, size_t stride_px,
+                                    const unsigned* __restrict__ local_index, int parts, int tiles_x, int width, int height)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= width || y >= height) return;
+    const int tx = x / RT_TILE_W, ty = y / RT_TILE_H;
+    const int owner = rt_tile_owner(tx, ty, parts);
+    const unsigned li = local_index[ty * tiles_x + tx];
+    const int p = (y % RT_TILE_H) * RT_TILE_W + (x % RT_TILE_W);
+    frame[(size_t)y * width + x] = gathered[(size_t)owner * stride_px + (size_t)li * RT_TILE_PIXELS + p];
+}
+
+// ------------------------------------------------------------------ tiles
+inline int tiles_x_of(int w) { return (w + RT_TILE_W - 1) / RT_TILE_W; }
+inline int tiles_y_of(int h) { return (h + RT_TILE_H - 1) / RT_TILE_H; }
+
+void make_tile_list(int w, int h, int part, int parts, std::vector<unsigned>& out)
+{
+    out.clear();
+    const int tx_n = tiles_x_of(w), ty_n = tiles_y_of(h);
+    for (int ty = 0; ty < ty_n; ty++)
+        for (int tx = 0; tx < tx_n; tx++)
+            if (rt_tile_owner(tx, ty, parts) == part) out.push_back((unsigned)(ty * tx_n + tx));
+}
+
+template <class T>
+int ensure(rt_ctx* c, T** p, size_t* cap, size_t need)
+{
+    if (*cap >= need && *p) return RT_OK;
+    if (*p) CK(c, cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    CK(c, cudaMalloc((void**)p, need * sizeof(T)));
+    *cap = need;
+    return RT_OK;
+}
+
+int setup_tiles(rt_ctx* c, int w, int h, int part_index, int part_count)
+{
+    const int nd = (int)c->devs.size();
+    const int parts = part_count * nd;
+    if (c->tl_w == w && c->tl_h == h && c->tl_parts == parts && c->tl_index == part_index) return RT_OK;
+    std::vector<unsigned> tl;
+    for (int d = 0; d < nd; d++) {
+        Dev& D = c->devs[d];
+        make_tile_list(w, h, part_index * nd + d, parts, tl);
+        CK(c, cudaSetDevice(D.id));
+        int rc = ensure(c, &D.tile_list, &D.tile_cap, std::max<size_t>(tl.size(), 1));
+        if (rc) return rc;
+        if (!tl.empty()) CK(c, cudaMemcpyAsync(D.tile_list, tl.data(), tl.size() * 4, cudaMemcpyHostToDevice, D.stream));
+        CK(c, cudaStreamSynchronize(D.stream)); // tl is reused by the next iteration
+        D.n_tiles = (int)tl.size();
+    }
+    c->tl_w = w; c->tl_h = h; c->tl_parts = parts; c->tl_index = part_index;
+    return RT_OK;
+}
+
+int setup_local_index(rt_ctx* c, int w, int h, int parts)
+{
+    if (c->li_w == w && c->li_h == h && c->li_parts == parts && c->local_index) return RT_OK;
+    const int tx_n = tiles_x_of(w), ty_n = tiles_y_of(h);
+    std::vector<unsigned> li((size_t)tx_n * ty_n), next((size_t)parts, 0u);
+    for (int ty = 0; ty < ty_n; ty++)
+        for (int tx = 0; tx < tx_n; tx++) li[(size_t)ty * tx_n + tx] = next[rt_tile_owner(tx, ty, parts)]++;
+    Dev& D0 = c->devs[0];
+    CK(c, cudaSetDevice(D0.id));
+    int rc = ensure(c, &c->local_index, &c->local_index_cap, li.size());
+    if (rc) return rc;
+    CK(c, cudaMemcpy(c->local_index, li.data(), li.size() * 4, cudaMemcpyHostToDevice));
+    c->li_w = w; c->li_h = h; c->li_parts = parts;
+    return RT_OK;
+}
+
+void free_dev(Dev& D)
+{
+    cudaSetDevice(D.id);
+    cudaFree(D.nodes); cudaFree(D.tris); cudaFree(D.shade); cudaFree(D.mats); cudaFree(D.lights);
+    cudaFree(D.tri_orig); cudaFree(D.leaf_cnt); cudaFree(D.ctrl); cudaFree(D.tile_list);
+    cudaFree(D.bgra); cudaFree(D.packed); cudaFree(D.rgb); cudaFree(D.tri_id); cudaFree(D.depth);
+    if (D.ctrl_host) cudaFreeHost(D.ctrl_host);
+    if (D.ev0) cudaEventDestroy(D.ev0);
+    if (D.ev1) cudaEventDestroy(D.ev1);
+    if (D.ev2) cudaEventDestroy(D.ev2);
+    if (D.stream) cudaStreamDestroy(D.stream);
+}
+
+} // namespace
+
+extern "C" {
+
+int rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+
+int rt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* rt_last_error(const rt_ctx* ctx) { return ctx ? ctx->err.c_str() : rt::get_error(); }
+
+void rt_render_params_default(rt_render_params* p)
+{
+    if (!p) return;
+    std::memset(p, 0, sizeof *p);
+    p->cam.pos[0] = 0; p->cam.pos[1] = -9; p->cam.pos[2] = 3;      // cpu/src/main.c:105
+    p->cam.rot[0] = (float)(-3.14159265358979323846 / 12);          // cpu/src/main.c:106
+    p->cam.fov = (float)(3.14159265358979323846 / 3.2);             // cpu/src/main.c:105
+    p->width = 1920; p->height = 1080;                              // cpu/include/options.h:6-7
+    p->spp = 1; p->seed = 1;
+    p->bounces = 4;                                                 // cpu/include/options.h:52
+    p->mode = RT_MODE_FAST;
+    p->gather = RT_GATHER_PEER_STORE;
+    p->part_index = 0; p->part_count = 1;
+}
+
+int rt_part_tile_count(int width, int height, int part_index, int part_count)
+{
+    if (width < 1 || height < 1 || part_count < 1 || part_index < 0 || part_index >= part_count) return RT_ERR_INVALID;
+    const int tx_n = tiles_x_of(width), ty_n = tiles_y_of(height);
+    int n = 0;
+    for (int ty = 0; ty < ty_n; ty++)
+        for (int tx = 0; tx < tx_n; tx++) n += rt_tile_owner(tx, ty, part_count) == part_index;
+    return n;
+}
+
+int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** out)
+{
+    if (!desc || !out) return fail(nullptr, RT_ERR_INVALID, "rt_create: null argument");
+    *out = nullptr;
+    int avail = rt_device_count();
+    if (avail <= 0) return fail(nullptr, RT_ERR_NO_DEVICE, "rt_create: no CUDA device available (this library has no CPU fallback)");
+    int dflt = 0;
+    if (!devices || ndev <= 0) { devices = &dflt; ndev = 1; }
+    if (ndev > RT_MAX_DEVICES) return fail(nullptr, RT_ERR_INVALID, "rt_create: too many devices");
+    for (int i = 0; i < ndev; i++)
+        if (devices[i] < 0 || devices[i] >= avail) return fail(nullptr, RT_ERR_INVALID, "rt_create: device index out of range");
+
+    rt::FlatScene flat;
+    std::string err;
+    int rc = rt::flatten_scene(*desc, flat, err);
+    if (rc) return fail(nullptr, rc, "rt_create: " + err);
+
+    rt_ctx* c = new rt_ctx();
+    c->scene_bytes = flat.bytes();
+    c->scene_host_view.n_lights = (int)flat.n_lights;
+    std::memcpy(c->scene_host_view.amb, flat.ambient, 12);
+    c->devs.resize(ndev);
+    auto bail = [&](int code) { for (Dev& D : c->devs) free_dev(D); std::string m = c->err; delete c; rt::set_error(m); return code; };
+#define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { c->err = std::string(#call) + " failed: " + cudaGetErrorString(e__); return bail(RT_ERR_CUDA); } } while (0)
+    for (int i = 0; i < ndev; i++) {
+        Dev& D = c->devs[i];
+        D.id = devices[i];
+        CKC(cudaSetDevice(D.id));
+        cudaDeviceProp prop;
+        CKC(cudaGetDeviceProperties(&prop, D.id));
+        D.sm_count = prop.multiProcessorCount;
+        CKC(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
+        CKC(cudaEventCreate(&D.ev0)); CKC(cudaEventCreate(&D.ev1)); CKC(cudaEventCreate(&D.ev2));
+        CKC(upload(&D.nodes, flat.nodes.data(), flat.nodes.size() * 4, D.stream));
+        CKC(upload(&D.tris, flat.tris.data(), flat.tris.size() * 4, D.stream));
+        CKC(upload(&D.tri_orig, flat.tri_orig.data(), flat.tri_orig.size() * 4, D.stream));
+        CKC(upload(&D.shade, flat.shade.data(), flat.shade.size() * 4, D.stream));
+        CKC(upload(&D.mats, flat.mats.data(), flat.mats.size() * 4, D.stream));
+        CKC(upload(&D.lights, flat.lights.data(), flat.lights.size() * 4, D.stream));
+        CKC(upload(&D.leaf_cnt, flat.leaf_cnt.data(), flat.leaf_cnt.size() * 4, D.stream));
+        CKC(cudaMalloc((void**)&D.ctrl, 64));
+        CKC(cudaMallocHost((void**)&D.ctrl_host, 64));
+        CKC(cudaStreamSynchronize(D.stream));
+        if (i > 0) { // NVLink / NVSwitch peer mapping towards the frame owner
+            int can = 0;
+            CKC(cudaDeviceCanAccessPeer(&can, D.id, c->devs[0].id));
+            if (can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(c->devs[0].id, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+                CKC(e);
+                D.peer_to_0 = true;
+            }
+        }
+    }
+#undef CKC
+    *out = c;
+    return RT_OK;
+}
+
+void rt_destroy(rt_ctx* c)
+{
+    if (!c) return;
+    if (c->ipc_frame) { cudaSetDevice(c->devs[0].id); cudaIpcCloseMemHandle(c->ipc_frame); }
+    if (!c->devs.empty()) { cudaSetDevice(c->devs[0].id); cudaFree(c->local_index); cudaFree(c->gather_buf); }
+    for (Dev& D : c->devs) free_dev(D);
+    delete c;
+}
+
+int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
+{
+    if (!c || !p) return fail(c, RT_ERR_INVALID, "rt_render: null argument");
+    if (p->width < 1 || p->height < 1 || p->width > 65535 || p->height > 32767) return fail(c, RT_ERR_INVALID, "rt_render: bad resolution");
+    if (p->spp < 1) return fail(c, RT_ERR_INVALID, "rt_render: spp must be >= 1");
+    if (p->bounces > RT_MAX_BOUNCES) return fail(c, RT_ERR_INVALID, "rt_render: bounces > 8");
+    if (p->mode != RT_MODE_FAST && p->mode != RT_MODE_STRICT) return fail(c, RT_ERR_INVALID, "rt_render: bad mode");
+    const int part_count = p->part_count < 1 ? 1 : p->part_count;
+    if (p->part_index < 0 || p->part_index >= part_count) return fail(c, RT_ERR_INVALID, "rt_render: bad partition");
+    const int nd = (int)c->devs.size();
+    const int w = p->width, h = p->height;
+    const size_t npx = (size_t)w * h;
+    int gather = p->gather;
+    for (int d = 1; d < nd; d++)
+        if (!c->devs[d].peer_to_0) gather = RT_GATHER_PEER_COPY; // no NVLink mapping: staged copies
+    if (nd > 1 && gather == RT_GATHER_PEER_COPY && (p->aov_mask & (RT_AOV_RGB_F32 | RT_AOV_TRI_ID | RT_AOV_DEPTH)))
+        for (int d = 1; d < nd; d++)
+            if (!c->devs[d].peer_to_0) return fail(c, RT_ERR_INVALID, "rt_render: AOVs on several devices need peer access");
+    if (c->ipc_frame && (c->ipc_w != w || c->ipc_h != h)) return fail(c, RT_ERR_STATE, "rt_render: imported frame has another size");
+    if (nd > 1 && part_count > 1) return fail(c, RT_ERR_INVALID, "rt_render: use either several devices per context or part_count > 1");
+
+    int rc = setup_tiles(c, w, h, p->part_index, part_count);
+    if (rc) return rc;
+
+    // frame storage on device 0 (+ local frames for PEER_COPY)
+    Dev& D0 = c->devs[0];
+    CK(c, cudaSetDevice(D0.id));
+    if ((rc = ensure(c, &D0.bgra, &D0.bgra_px, npx))) return rc;
+    if (p->aov_mask & RT_AOV_RGB_F32) { if ((rc = ensure(c, &D0.rgb, &D0.aov_px[0], 3 * npx))) return rc; }
+    if (p->aov_mask & RT_AOV_TRI_ID) { if ((rc = ensure(c, &D0.tri_id, &D0.aov_px[1], npx))) return rc; }
+    if (p->aov_mask & RT_AOV_DEPTH) { if ((rc = ensure(c, &D0.depth, &D0.aov_px[2], npx))) return rc; }
+    if (nd > 1 && gather == RT_GATHER_PEER_COPY) {
+        for (int d = 1; d < nd; d++) {
+            Dev& D = c->devs[d];
+            CK(c, cudaSetDevice(D.id));
+            if ((rc = ensure(c, &D.bgra, &D.bgra_px, npx))) return rc;
+            if ((rc = ensure(c, &D.packed, &D.packed_px, std::max<size_t>((size_t)D.n_tiles * RT_TILE_PIXELS, 1)))) return rc;
+        }
+    }
+
+    rt::CameraBasis cb;
+    rt::camera_basis(p->cam, w, h, cb);
+
+    RtFrameArgs fa;
+    std::memset(&fa, 0, sizeof fa);
+    std::memcpy(fa.pos, cb.pos, 12); std::memcpy(fa.ul, cb.ul, 12);
+    std::memcpy(fa.inc_x, cb.inc_x, 12); std::memcpy(fa.inc_y, cb.inc_y, 12);
+    fa.width = w; fa.height = h; fa.spp = p->spp; fa.bounces = p->bounces; fa.seed = p->seed;
+    fa.tiles_x = tiles_x_of(w);
+
+    RtLaunchCfg cfg;
+    cfg.block_threads = p->block_threads == 64 ? 64 : 128;
+    cfg.min_ctas = p->ctas_per_sm > 0 ? p->ctas_per_sm : (cfg.block_threads == 64 ? 8 : 4);
+    cfg.work_counters = (p->aov_mask & RT_AOV_WORK) != 0;
+    fa.refill_threshold = p->refill_threshold > 0 ? std::min(p->refill_threshold, 32) : 20;
+
+    unsigned launches = 0;
+    if (p->bounces <= 0) {
+        // BOUNCES == 0: raytrace returns black before any traversal (cpu/src/raytracer.c:104-105)
+        CK(c, cudaSetDevice(D0.id));
+        uchar4* target = c->ipc_frame ? c->ipc_frame : D0.bgra;
+        fill_bgra_kernel<<<D0.sm_count * 4, 256, 0, D0.stream>>>(target, npx, make_uchar4(0, 0, 0, 255));
+        CK(c, cudaGetLastError());
+        if (p->aov_mask & RT_AOV_RGB_F32) CK(c, cudaMemsetAsync(D0.rgb, 0, 12 * npx, D0.stream));
+        if (p->aov_mask & RT_AOV_TRI_ID) CK(c, cudaMemsetAsync(D0.tri_id, 0xff, 4 * npx, D0.stream));
+        if (p->aov_mask & RT_AOV_DEPTH) CK(c, cudaMemsetAsync(D0.depth, 0, 4 * npx, D0.stream));
+        CK(c, cudaStreamSynchronize(D0.stream));
+        if (tm) { std::memset(tm, 0, sizeof *tm); tm->launches = 1; tm->n_devices = nd; }
+        c->width = w; c->height = h; c->aov_mask = p->aov_mask; c->rendered = true;
+        c->part_index = p->part_index; c->part_count = part_count;
+        return RT_OK;
+    }
+
+    // ---- launch on every device ----
+    for (int d = 0; d < nd; d++) {
+        Dev& D = c->devs[d];
+        CK(c, cudaSetDevice(D.id));
+        RtDeviceScene sc = c->scene_host_view;
+        sc.nodes = D.nodes; sc.tris = D.tris; sc.tri_orig = D.tri_orig; sc.shade = D.shade;
+        sc.mats = D.mats; sc.lights = D.lights; sc.leaf_cnt = D.leaf_cnt;
+        RtFrameArgs f = fa;
+        f.tile_list = D.tile_list; f.n_tiles = D.n_tiles;
+        f.stats = D.ctrl; f.tile_counter = reinterpret_cast<unsigned*>(D.ctrl + 4);
+        const bool local = (d > 0 && gather == RT_GATHER_PEER_COPY);
+        f.bgra = local ? D.bgra : (c->ipc_frame ? c->ipc_frame : D0.bgra); // peer-mapped for d > 0
+        f.rgb = (p->aov_mask & RT_AOV_RGB_F32) ? D0.rgb : nullptr;
+        f.tri_id = (p->aov_mask & RT_AOV_TRI_ID) ? D0.tri_id : nullptr;
+        f.depth = (p->aov_mask & RT_AOV_DEPTH) ? D0.depth : nullptr;
+
+        int occ = 0, regs = 0;
+        cudaError_t e = (p->mode == RT_MODE_STRICT) ? rt_occupancy_strict(cfg, &occ, &regs) : rt_occupancy_fast(cfg, &occ, &regs);
+        CK(c, e);
+        if (occ < 1) return fail(c, RT_ERR_CUDA, "rt_render: kernel does not fit on an SM");
+        RtLaunchCfg cf = cfg;
+        cf.grid = D.sm_count * occ; // persistent: exactly one resident wave
+        const int warps_needed = (D.n_tiles * RT_TILE_PIXELS / 32 + (cf.block_threads / 32) - 1) / (cf.block_threads / 32);
+        if (warps_needed < cf.grid) cf.grid = std::max(warps_needed, 1);
+
+        CK(c, cudaMemsetAsync(D.ctrl, 0, 64, D.stream));
+        CK(c, cudaEventRecord(D.ev0, D.stream));
+        e = (p->mode == RT_MODE_STRICT) ? rt_launch_strict(sc, f, cf, D.stream) : rt_launch_fast(sc, f, cf, D.stream);
+        CK(c, e);
+        CK(c, cudaEventRecord(D.ev1, D.stream));
+        launches++;
+        CK(c, cudaMemcpyAsync(D.ctrl_host, D.ctrl, 32, cudaMemcpyDeviceToHost, D.stream));
+    }
+
+    // ---- unfused gather: pack on each device, copy to device 0, unpack ----
+    float gather_ms = 0.f;
+    if (nd > 1 && gather == RT_GATHER_PEER_COPY) {
+        const int parts = part_count * nd;
+        if ((rc = setup_local_index(c, w, h, parts))) return rc;
+        size_t stride = 0;
+        for (int d = 0; d < nd; d++) stride = std::max(stride, (size_t)c->devs[d].n_tiles * RT_TILE_PIXELS);
+        CK(c, cudaSetDevice(D0.id));
+        if ((rc = ensure(c, &c->gather_buf, &c->gather_px, stride * parts))) return rc;
+        if ((rc = ensure(c, &D0.packed, &D0.packed_px, std::max<size_t>((size_t)D0.n_tiles * RT_TILE_PIXELS, 1)))) return rc;
+        for (int d = 1; d < nd; d++) {
+            Dev& D = c->devs[d];
+            CK(c, cudaSetDevice(D.id));
+            if (D.n_tiles) {
+                pack_tiles_kernel<<<D.n_tiles, RT_TILE_PIXELS, 0, D.stream>>>(D.bgra, D.packed, D.tile_list, D.n_tiles, fa.tiles_x, w, h);
+                CK(c, cudaGetLastError());
+                launches++;
+                CK(c, cudaMemcpyPeerAsync(c->gather_buf + stride * (size_t)(p->part_index * nd + d), D0.id, D.packed, D.id,
+                                          (size_t)D.n_tiles * RT_TILE_PIXELS * 4, D.stream));
+            }
+            CK(c, cudaEventRecord(D.ev2, D.stream));
+        }
+        CK(c, cudaSetDevice(D0.id));
+        for (int d = 1; d < nd; d++) CK(c, cudaStreamWaitEvent(D0.stream, c->devs[d].ev2, 0));
+        CK(c, cudaEventRecord(D0.ev2, D0.stream));
+        // device 0's own tiles are already in place; scatter the others (device 0's slot is skipped by
+        // packing its own tiles too, which keeps the unpack kernel branch-free)
+        if (D0.n_tiles) {
+            pack_tiles_kernel<<<D0.n_tiles, RT_TILE_PIXELS, 0, D0.stream>>>(D0.bgra, D0.packed, D0.tile_list, D0.n_tiles, fa.tiles_x, w, h);
+            CK(c, cudaGetLastError());
+            launches++;
+            CK(c, cudaMemcpyAsync(c->gather_buf + stride * (size_t)(p->part_index * nd), D0.packed, (size_t)D0.n_tiles * RT_TILE_PIXELS * 4,
+                                  cudaMemcpyDeviceToDevice, D0.stream));
+        }
+        dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
+        unpack_tiles_kernel<<<grd, blk, 0, D0.stream>>>(D0.bgra, c->gather_buf, stride, c->local_index, parts, fa.tiles_x, w, h);
+        CK(c, cudaGetLastError());
+        launches++;
+        cudaEvent_t done;
+        CK(c, cudaEventCreate(&done));
+        CK(c, cudaEventRecord(done, D0.stream));
+        CK(c, cudaEventSynchronize(done));
+        // gather time = slowest (pack + NVLink copy) of the other devices + (pack + unpack) on device 0
+        CK(c, cudaEventElapsedTime(&gather_ms, D0.ev2, done));
+        CK(c, cudaEventDestroy(done));
+        float worst = 0.f;
+        for (int d = 1; d < nd; d++) {
+            float t_d = 0.f;
+            CK(c, cudaSetDevice(c->devs[d].id));
+            CK(c, cudaEventSynchronize(c->devs[d].ev2));
+            CK(c, cudaEventElapsedTime(&t_d, c->devs[d].ev1, c->devs[d].ev2));
+            worst = std::max(worst, t_d);
+        }
+        gather_ms += worst;
+    }
+
+    // ---- completion + timing ----
+    rt_timing t;
+    std::memset(&t, 0, sizeof t);
+    float kmax = 0.f;
+    for (int d = 0; d < nd; d++) {
+        Dev& D = c->devs[d];
+        CK(c, cudaSetDevice(D.id));
+        CK(c, cudaStreamSynchronize(D.stream));
+        CK(c, cudaEventElapsedTime(&t.kernel_ms[d], D.ev0, D.ev1));
+        kmax = std::max(kmax, t.kernel_ms[d]);
+        t.rays_closest += D.ctrl_host[0];
+        t.rays_shadow += D.ctrl_host[1];
+        t.inner_visits += D.ctrl_host[2];
+        t.tri_tests += D.ctrl_host[3];
+    }
+    t.gather_ms = gather_ms;
+    t.total_ms = kmax + gather_ms;
+    t.launches = launches;
+    t.n_devices = (uint32_t)nd;
+    if (tm) *tm = t;
+    c->width = w; c->height = h; c->aov_mask = p->aov_mask; c->rendered = true;
+    c->part_index = p->part_index; c->part_count = part_count;
+    return RT_OK;
+}
+
+int rt_download(rt_ctx* c, uint8_t* bgra, float* rgb, int32_t* tri_id, float* depth_t)
+{
+    if (!c) return fail(c, RT_ERR_INVALID, "rt_download: null context");
+    if (!c->rendered) return fail(c, RT_ERR_STATE, "rt_download: nothing rendered yet");
+    Dev& D0 = c->devs[0];
+    const size_t npx = (size_t)c->width * c->height;
+    CK(c, cudaSetDevice(D0.id));
+    if (rgb && !(c->aov_mask & RT_AOV_RGB_F32)) return fail(c, RT_ERR_STATE, "rt_download: RT_AOV_RGB_F32 was not rendered");
+    if (tri_id && !(c->aov_mask & RT_AOV_TRI_ID)) return fail(c, RT_ERR_STATE, "rt_download: RT_AOV_TRI_ID was not rendered");
+    if (depth_t && !(c->aov_mask & RT_AOV_DEPTH)) return fail(c, RT_ERR_STATE, "rt_download: RT_AOV_DEPTH was not rendered");
+    if (bgra) CK(c, cudaMemcpyAsync(bgra, c->ipc_frame ? c->ipc_frame : D0.bgra, npx * 4, cudaMemcpyDeviceToHost, D0.stream));
+    if (rgb) CK(c, cudaMemcpyAsync(rgb, D0.rgb, npx * 12, cudaMemcpyDeviceToHost, D0.stream));
+    if (tri_id) CK(c, cudaMemcpyAsync(tri_id, D0.tri_id, npx * 4, cudaMemcpyDeviceToHost, D0.stream));
+    if (depth_t) CK(c, cudaMemcpyAsync(depth_t, D0.depth, npx * 4, cudaMemcpyDeviceToHost, D0.stream));
+    CK(c, cudaStreamSynchronize(D0.stream));
+    return RT_OK;
+}
+
+int rt_frame_device_ptr(rt_ctx* c, void** dev_ptr, size_t* bytes)
+{
+    if (!c || !dev_ptr) return fail(c, RT_ERR_INVALID, "rt_frame_device_ptr: null argument");
+    if (!c->rendered) return fail(c, RT_ERR_STATE, "rt_frame_device_ptr: nothing rendered yet");
+    *dev_ptr = c->ipc_frame ? c->ipc_frame : c->devs[0].bgra;
+    if (bytes) *bytes = (size_t)c->width * c->height * 4;
+    return RT_OK;
+}
+
+int rt_packed_tiles(rt_ctx* c, void** dev_ptr, size_t* bytes)
+{
+    if (!c || !dev_ptr) return fail(c, RT_ERR_INVALID, "rt_packed_tiles: null argument");
+    if (!c->rendered) return fail(c, RT_ERR_STATE, "rt_packed_tiles: nothing rendered yet");
+    if (c->devs.size() != 1) return fail(c, RT_ERR_STATE, "rt_packed_tiles: one device per context expected");
+    Dev& D = c->devs[0];
+    CK(c, cudaSetDevice(D.id));
+    int rc = ensure(c, &D.packed, &D.packed_px, std::max<size_t>((size_t)D.n_tiles * RT_TILE_PIXELS, 1));
+    if (rc) return rc;
+    if (D.n_tiles) {
+        pack_tiles_kernel<<<D.n_tiles, RT_TILE_PIXELS, 0, D.stream>>>(D.bgra, D.packed, D.tile_list, D.n_tiles, tiles_x_of(c->width), c->width, c->height);
+        CK(c, cudaGetLastError());
+    }
+    CK(c, cudaStreamSynchronize(D.stream));
+    *dev_ptr = D.packed;
+    if (bytes) *bytes = (size_t)D.n_tiles * RT_TILE_PIXELS * 4;
+    return RT_OK;
+}
+
+int rt_unpack_tiles(rt_ctx* c, const void* dev_gathered, size_t stride_bytes, int part_count)
+{
+    if (!c || !dev_gathered || part_count < 1 || stride_bytes % 4) return fail(c, RT_ERR_INVALID, "rt_unpack_tiles: bad argument");
+    if (!c->rendered) return fail(c, RT_ERR_STATE, "rt_unpack_tiles: nothing rendered yet");
+    Dev& D0 = c->devs[0];
+    const int w = c->width, h = c->height;
+    int rc = setup_local_index(c, w, h, part_count);
+    if (rc) return rc;
+    CK(c, cudaSetDevice(D0.id));
+    dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
+    unpack_tiles_kernel<<<grd, blk, 0, D0.stream>>>(D0.bgra, static_cast<const uchar4*>(dev_gathered), stride_bytes / 4, c->local_index,
+                                                    part_count, tiles_x_of(w), w, h);
+    CK(c, cudaGetLastError());
+    CK(c, cudaStreamSynchronize(D0.stream));
+    return RT_OK;
+}
+
+int rt_frame_ipc_export(rt_ctx* c, int width, int height, void* handle64)
+{
+    if (!c || !handle64 || width < 1 || height < 1) return fail(c, RT_ERR_INVALID, "rt_frame_ipc_export: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    Dev& D0 = c->devs[0];
+    CK(c, cudaSetDevice(D0.id));
+    int rc = ensure(c, &D0.bgra, &D0.bgra_px, (size_t)width * height);
+    if (rc) return rc;
+    cudaIpcMemHandle_t hnd;
+    CK(c, cudaIpcGetMemHandle(&hnd, D0.bgra));
+    std::memcpy(handle64, &hnd, 64);
+    return RT_OK;
+}
+
+int rt_frame_ipc_import(rt_ctx* c, const void* handle64, int width, int height)
+{
+    if (!c || !handle64 || width < 1 || height < 1) return fail(c, RT_ERR_INVALID, "rt_frame_ipc_import: bad argument");
+    Dev& D0 = c->devs[0];
+    CK(c, cudaSetDevice(D0.id));
+    if (c->ipc_frame) { CK(c, cudaIpcCloseMemHandle(c->ipc_frame)); c->ipc_frame = nullptr; }
+    cudaIpcMemHandle_t hnd;
+    std::memcpy(&hnd, handle64, 64);
+    void* p = nullptr;
+    CK(c, cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+    c->ipc_frame = static_cast<uchar4*>(p);
+    c->ipc_w = width; c->ipc_h = height;
+    return RT_OK;
+}
+
+} // extern "C"

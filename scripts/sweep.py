@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Launch-parameter sweep of the render kernel on one GPU (the analogue of the reference's .bat block
+sweeps, gpu/*.bat): prints median kernel ms (L2 warm, CUDA events) per configuration as JSON lines."""
+import itertools
+import json
+import statistics
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import parallel_ray_tracer_b200 as rt  # noqa: E402
+
+
+def main():
+    frames = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    cases = [("car_only", 1920, 1080), ("car_boxed", 1920, 1080), ("car_boxed", 3840, 2160)]
+    for scene, w, h in cases:
+        sc = rt.Scene.load_rtsc(ROOT / "tests" / "golden" / "scenes" / f"{scene}.rtsc").build_bvh(6)
+        ctx = rt.Context(sc, [0])
+        for mode in (rt.RT_MODE_FAST, rt.RT_MODE_STRICT):
+            grid = [(128, c, r) for c in (3, 4, 5, 6, 8) for r in (8, 16, 20, 24, 28, 32)] + [(64, c, r) for c in (8, 12, 16) for r in (16, 24)]
+            if mode == rt.RT_MODE_STRICT:
+                grid = [(128, 4, 20), (128, 5, 24)]
+            for block, ctas, refill in grid:
+                p = rt.default_params(width=w, height=h, mode=mode, block_threads=block, ctas_per_sm=ctas, refill_threshold=refill)
+                ms = []
+                for i in range(frames + 3):
+                    tm = ctx.render_frame(p)
+                    if i >= 3:
+                        ms.append(tm.kernel_ms[0])
+                rays = tm.rays_closest + tm.rays_shadow
+                med = statistics.median(ms)
+                print(json.dumps({"scene": scene, "w": w, "h": h, "mode": "strict" if mode else "fast", "block": block, "ctas_per_sm": ctas,
+                                  "refill": refill, "kernel_ms_median": round(med, 4), "kernel_ms_min": round(min(ms), 4),
+                                  "mrays_s": round(rays / med / 1e3, 1), "rays": rays}), flush=True)
+        ctx.close()
+
+
+if __name__ == "__main__":
+    main()

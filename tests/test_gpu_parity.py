@@ -1,0 +1,247 @@
+"""Parity of the CUDA render path (through the C-ABI) against the CPU oracle and against AOVs
+produced by the reference itself.  Bars (BASELINE.json north_star):
+  RT_MODE_STRICT  bit-exact first-hit ID, depth t, float RGB and 8-bit BGRA vs oracle/rt_oracle.c
+  RT_MODE_FAST    first-hit ID >= 99.99 %, 8-bit RGB within 1 LSB on >= 99.9 %, depth within 1e-4
+                  relative (on >= 99.99 % of pixels; the remainder are ID ties at silhouette edges)
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import SCENES, cam_of, load_gold
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _need_gpu(rt):
+    if rt.device_count() < 1:
+        pytest.skip("no CUDA device")
+
+AOV_ALL = 1 | 2 | 4
+
+
+def render(rt, ctx, w, h, mode, cam=None, **kw):
+    p = rt.default_params(width=w, height=h, mode=mode, aov_mask=kw.pop("aov_mask", AOV_ALL), cam=cam, **kw)
+    tm = ctx.render_frame(p)
+    out = ctx.load_from_gpu(rgb=True, tri_id=True, depth=True)
+    out["timing"] = tm
+    return out
+
+
+def assert_fast_parity(m, ids=0.9999, rgb=0.999, dep=0.9999):
+    assert m["id_match"] >= ids, m
+    assert m["rgb8_within1"] >= rgb, m
+    assert m["depth_within_1e-4"] >= dep, m
+
+
+@pytest.mark.parametrize("scene", SCENES)
+@pytest.mark.parametrize("cam", ["default", "yaw"])
+@pytest.mark.parametrize("wh", [(160, 90), (480, 270)])
+def test_strict_is_bit_exact_vs_oracle(rt, gpu_scenes, oracle_scenes, manifest, scene, cam, wh):
+    w, h = wh
+    pos, rot, fov = cam_of(manifest, cam)
+    ref = oracle_scenes[scene].render(w, h, pos=pos, rot=rot, fov=fov)
+    got = render(rt, gpu_scenes[scene][1], w, h, rt.RT_MODE_STRICT, cam=(pos, rot, fov))
+    assert np.array_equal(got["id"], ref["id"])
+    assert np.array_equal(got["depth"].view(np.uint32), ref["depth"].view(np.uint32))
+    assert np.array_equal(got["rgb"].view(np.uint32), ref["rgb"].view(np.uint32))
+    assert np.array_equal(got["bgra"], ref["bgra"])
+    tm = got["timing"]
+    assert (tm.rays_closest, tm.rays_shadow) == (ref["rays_closest"], ref["rays_shadow"])
+
+
+@pytest.mark.parametrize("scene", SCENES)
+@pytest.mark.parametrize("cam", ["default", "yaw"])
+def test_fast_vs_oracle(rt, gpu_scenes, oracle_scenes, manifest, scene, cam):
+    w, h = 640, 360
+    pos, rot, fov = cam_of(manifest, cam)
+    ref = oracle_scenes[scene].render(w, h, pos=pos, rot=rot, fov=fov)
+    got = render(rt, gpu_scenes[scene][1], w, h, rt.RT_MODE_FAST, cam=(pos, rot, fov))
+    assert_fast_parity(O.compare_aovs(got, ref))
+    tm = got["timing"]
+    n_ref = ref["rays_closest"] + ref["rays_shadow"]
+    assert abs((tm.rays_closest + tm.rays_shadow) - n_ref) <= 1e-3 * n_ref  # ray counts follow hit decisions
+
+
+@pytest.mark.parametrize("scene", SCENES)
+@pytest.mark.parametrize("cam", ["default", "yaw"])
+@pytest.mark.parametrize("mode", ["fast", "strict"])
+def test_vs_reference_golden_aovs(rt, gpu_scenes, manifest, scene, cam, mode):
+    """Against AOVs computed by the reference's own bvh_traverse/raytrace (tests/golden)."""
+    gold = load_gold(f"ref_{scene}_{cam}_160x90.npz")
+    got = render(rt, gpu_scenes[scene][1], 160, 90, rt.RT_MODE_FAST if mode == "fast" else rt.RT_MODE_STRICT,
+                 cam=cam_of(manifest, cam))
+    assert_fast_parity(O.compare_aovs(got, gold), ids=0.9995, dep=0.9995)  # 14 400 px: <= 7 tie pixels
+
+
+def test_work_counters_match_oracle(rt, gpu_scenes, oracle_scenes):
+    """RT_AOV_WORK: inner-node visits and triangle tests equal the oracle's (reference visit order)."""
+    w, h = 320, 180
+    for scene in ("car_only", "car_boxed"):
+        ref = oracle_scenes[scene].render(w, h)
+        got = render(rt, gpu_scenes[scene][1], w, h, rt.RT_MODE_STRICT, aov_mask=AOV_ALL | rt.RT_AOV_WORK)
+        tm = got["timing"]
+        assert tm.inner_visits == ref["inner_visits"] and tm.tri_tests == ref["tri_tests"]
+        assert np.array_equal(got["bgra"], ref["bgra"])
+
+
+@pytest.mark.parametrize("spp", [2, 4])
+def test_spp_strict_bit_exact_and_golden(rt, gpu_scenes, oracle_scenes, spp):
+    w, h = 96, 54
+    ref = oracle_scenes["car_only"].render(w, h, spp=spp, seed=7)
+    got = render(rt, gpu_scenes["car_only"][1], w, h, rt.RT_MODE_STRICT, spp=spp, seed=7)
+    assert np.array_equal(got["rgb"].view(np.uint32), ref["rgb"].view(np.uint32))
+    assert np.array_equal(got["bgra"], ref["bgra"])
+    assert np.array_equal(got["id"], ref["id"])   # AOVs come from sample 0 = the reference ray
+    if spp == 4:
+        gold = load_gold("ref_car_only_default_96x54_spp4.npz")
+        fast = render(rt, gpu_scenes["car_only"][1], w, h, rt.RT_MODE_FAST, spp=spp, seed=7)
+        d = np.abs(fast["bgra"].astype(int) - gold["bgra"].astype(int)).max(-1)
+        assert (d <= 1).mean() >= 0.999
+
+
+@pytest.mark.parametrize("bounces", [0, 1, 2, 3])
+def test_bounce_limits(rt, gpu_scenes, oracle_scenes, bounces):
+    w, h = 200, 112
+    ref = oracle_scenes["car_boxed"].render(w, h, bounces=bounces)
+    got = render(rt, gpu_scenes["car_boxed"][1], w, h, rt.RT_MODE_STRICT, bounces=bounces, aov_mask=1)
+    assert np.array_equal(got["bgra"], ref["bgra"])
+    if bounces == 0:
+        assert np.all(got["bgra"][..., :3] == 0) and np.all(got["bgra"][..., 3] == 255)
+
+
+@pytest.mark.parametrize("wh", [(250, 131), (17, 9), (1, 1), (16, 8), (33, 200)])
+def test_ragged_resolutions(rt, gpu_scenes, oracle_scenes, wh):
+    """Sizes that are not multiples of the 16x8 tile (edge tiles are partly outside the image)."""
+    w, h = wh
+    ref = oracle_scenes["car_only"].render(w, h)
+    got = render(rt, gpu_scenes["car_only"][1], w, h, rt.RT_MODE_STRICT)
+    assert np.array_equal(got["bgra"], ref["bgra"]) and np.array_equal(got["id"], ref["id"])
+
+
+def test_user_supplied_reference_tree(rt, scene_arrays, orc, manifest):
+    """Drop-in: a BVH built elsewhere (here: the oracle's restatement of the reference binary's tree,
+    whose digest is pinned in tests/golden/manifest.json) is accepted as is."""
+    sc_a = scene_arrays["car_only"]
+    s = orc.scene(sc_a)
+    nodes, ti = s.build_bvh(6 | 0x100)
+    lib_sc = rt.Scene.from_arrays(sc_a["tri"], sc_a["mat_idx"], sc_a["mats"], sc_a["lights"], sc_a["ambient"], nodes, ti)
+    ctx = rt.Context(lib_sc, [0])
+    ref = s.render(320, 180)
+    got = render(rt, ctx, 320, 180, rt.RT_MODE_STRICT)
+    assert np.array_equal(got["bgra"], ref["bgra"]) and np.array_equal(got["id"], ref["id"])
+    ctx.close()
+
+
+def test_degenerate_scenes(rt, orc):
+    """One triangle (the root is a leaf), and a scene whose only triangle is behind the camera."""
+    tri = np.array([[-2, 0, 1, 2, 0, 1, 0, 0, 4]], np.float32)
+    mats = np.array([[0.5, 0.5, 0.5, 0.7, 0.2, 0.1, 0.3, 0.3, 0.3]], np.float32)
+    lights = np.array([[0, -8, 3, 50, 50, 50]], np.float32)
+    for t in (tri, tri + np.array([0, -30, 0] * 3, np.float32)):
+        sc = rt.Scene.from_arrays(t, [0], mats, lights).build_bvh(6)
+        ctx = rt.Context(sc, [0])
+        s = orc.scene({"tri": t, "mat_idx": np.zeros(1, np.uint32), "mats": mats, "lights": lights, "ambient": [0.5] * 3})
+        s.build_bvh(6)
+        ref = s.render(64, 36)
+        got = render(rt, ctx, 64, 36, rt.RT_MODE_STRICT)
+        assert np.array_equal(got["bgra"], ref["bgra"]) and np.array_equal(got["id"], ref["id"])
+        ctx.close()
+
+
+def test_deep_leaf_with_many_triangles(rt, orc):
+    """Heuristic 0 on a soup hits the depth-32 cap and leaves big leaves (count escape path)."""
+    sc = rt.Scene.load_rtsc(O.HERE.parent / "tests" / "golden" / "scenes" / "soup2k.rtsc").build_bvh(0)
+    a = sc.arrays()
+    dt = np.dtype([("min", "3f4"), ("max", "3f4"), ("len", "i4"), ("idx", "i4")])
+    assert a["bvh_nodes"].view(dt)["len"].max() >= 15
+    ctx = rt.Context(sc, [0])
+    s = orc.scene(O.load_rtsc(O.HERE.parent / "tests" / "golden" / "scenes" / "soup2k.rtsc"))
+    s.set_bvh(a["bvh_nodes"], a["tri_idx"])
+    ref = s.render(120, 68)
+    got = render(rt, ctx, 120, 68, rt.RT_MODE_STRICT)
+    assert np.array_equal(got["bgra"], ref["bgra"]) and np.array_equal(got["id"], ref["id"])
+    ctx.close()
+
+
+# ---------------- full-size, size-independent properties (BASELINE.json configs) ----------------
+@pytest.mark.parametrize("scene,wh", [("car_only", (1920, 1080)), ("car_boxed", (1920, 1080)), ("car_boxed", (3840, 2160))])
+def test_full_size_properties(rt, gpu_scenes, manifest, scene, wh):
+    w, h = wh
+    ctx = gpu_scenes[scene][1]
+    fast = render(rt, ctx, w, h, rt.RT_MODE_FAST)
+    fast2 = render(rt, ctx, w, h, rt.RT_MODE_FAST)
+    strict = render(rt, ctx, w, h, rt.RT_MODE_STRICT)
+    # determinism: dynamic scheduling must not change a single byte
+    assert np.array_equal(fast["bgra"], fast2["bgra"]) and np.array_equal(fast["id"], fast2["id"])
+    # the fast build against the bit-exact build at full size
+    assert_fast_parity(O.compare_aovs(fast, strict))
+    # every pixel written exactly once: alpha is 255 everywhere, background is the ambient grey
+    assert np.all(strict["bgra"][..., 3] == 255)
+    miss = strict["id"] < 0
+    assert np.all(strict["bgra"][miss][:, :3] == 127)      # (uint8)(0.5 * 255)
+    assert np.all(strict["depth"][miss] == np.float32(3.4028234663852886e38))
+    # first-hit statistics of the reference's own 1080p frame
+    if wh == (1920, 1080):
+        g = manifest["scenes"][scene]["ref_1080p"]
+        assert abs(int((strict["id"] >= 0).sum()) - g["hit_pixels"]) <= 40
+        assert np.allclose(strict["rgb"].reshape(-1, 3).mean(0), g["mean_rgb"], atol=2e-5)
+    # ray accounting: rays per pixel
+    tm = strict["timing"]
+    rpp = (tm.rays_closest + tm.rays_shadow) / (w * h)
+    assert abs(rpp - (1.436 if scene == "car_only" else 6.389)) < 0.02
+    if (scene, wh) == ("car_only", (1920, 1080)):
+        assert (tm.rays_closest, tm.rays_shadow) == (2531859, 446673)
+    if (scene, wh) == ("car_boxed", (1920, 1080)):
+        assert (tm.rays_closest, tm.rays_shadow) == (6956560, 6291316)
+
+
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_partitioned_render_assembles_to_the_single_frame(rt, gpu_scenes, parts):
+    """N 'ranks' emulated sequentially on one GPU: each renders its interleaved tiles, the packed
+    buffers are concatenated (what NCCL all-gather produces) and unpacked: byte-identical frame."""
+    import ctypes as C
+    w, h = 500, 281
+    sc, ctx = gpu_scenes["car_boxed"]
+    full = render(rt, ctx, w, h, rt.RT_MODE_FAST)["bgra"]
+    from parallel_ray_tracer_b200 import partition as P
+    packed = []
+    for p in range(parts):
+        ctx.render_frame(rt.default_params(width=w, height=h, part_index=p, part_count=parts))
+        ptr, nbytes = ctx.packed_tiles()
+        assert nbytes == rt.part_tile_count(w, h, p, parts) * P.TILE_PIXELS * 4
+        # device -> host copy of the packed tiles through cudart (torch is only plumbing here)
+        import torch
+        t = torch.empty(nbytes, dtype=torch.uint8, device="cuda:0")
+        C.CDLL("libcudart.so").cudaMemcpy(C.c_void_p(t.data_ptr()), C.c_void_p(ptr), C.c_size_t(nbytes), 3)
+        packed.append(t.cpu().numpy())
+    assert np.array_equal(P.unpack(packed, w, h), full)
+    # and through the device-side unpack kernel
+    import torch
+    stride = max(len(b) for b in packed)
+    g = torch.zeros(parts * stride, dtype=torch.uint8, device="cuda:0")
+    for p, b in enumerate(packed):
+        g[p * stride:p * stride + len(b)] = torch.from_numpy(b).cuda()
+    torch.cuda.synchronize()
+    ctx.unpack_tiles(g.data_ptr(), stride, parts)
+    assert np.array_equal(ctx.load_from_gpu()["bgra"], full)
+
+
+def test_error_paths(rt, gpu_scenes):
+    sc, ctx = gpu_scenes["soup2k"]
+    with pytest.raises(rt.RtError):
+        ctx.render_frame(rt.default_params(width=0, height=10))
+    with pytest.raises(rt.RtError):
+        ctx.render_frame(rt.default_params(spp=0))
+    with pytest.raises(rt.RtError):
+        ctx.render_frame(rt.default_params(part_index=2, part_count=2))
+    ctx.render_frame(rt.default_params(width=32, height=16, aov_mask=0))
+    with pytest.raises(rt.RtError) as e:
+        ctx.load_from_gpu(depth=True)   # AOV not rendered
+    assert e.value.code == rt.RT_ERR_STATE
+    no_bvh = rt.Scene.load_rtsc(O.HERE.parent / "tests" / "golden" / "scenes" / "soup2k.rtsc")
+    with pytest.raises(rt.RtError):
+        rt.Context(no_bvh, [0])
+    with pytest.raises(rt.RtError):
+        rt.Context(sc, [99])

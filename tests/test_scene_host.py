@@ -1,0 +1,150 @@
+"""Host-side scene layer of the product (C++ behind the C-ABI): loaders, scene pack, BVH builder,
+BMP writer.  No GPU needed."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import GOLD, SCENES
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_obj_loader_rules(rt, tmp_path):
+    """The reference loader's rules (cpu/src/triangle.c:54-126) on a hand-written file."""
+    (tmp_path / "triangles.obj").write_text(
+        "# comment\nmtllib triangles.mtl.mtl\no Thing\n"
+        "v 0 0 0\nv 1 0 0\nv 0 1 0\nv 0 0 1\nvn 0 0 1\n"
+        "f 1 2 3\n"                 # before any usemtl: all-zero material
+        "usemtl red\nf 1 2 4\n"
+        "usemtl nosuch\nf 2 3 4\n"  # unknown name keeps the previous material
+        "s 0\nusemtl late\nf 1 3 4\n")
+    (tmp_path / "triangles.mtl").write_text(
+        "newmtl red\nNs 1\nKa 1 1 1\nKd 0.8 0.1 0.1\nKs 0.5 0.5 0.5\nKr 0.2 0.2 0.2\nKe 0 0 0\n\n"
+        "newmtl late\nNs 1\nKa 1 1 1\nKd 0.1 0.2 0.3\nKs 0.4 0.5 0.6\nKe 0 0 0\nKr 0.9 0.9 0.9\n")  # Kr on the 6th line: ignored
+    (tmp_path / "lights.obj").write_text("0 -8 3 50 50 50\n\n1 2 3 4 5 6")
+    sc = rt.Scene.load_dir(tmp_path)
+    a = sc.arrays()
+    assert a["tri"].shape == (4, 9)
+    assert np.array_equal(a["tri"][1], [0, 0, 0, 1, 0, 0, 0, 0, 1])
+    per_tri = a["mats"][a["mat_idx"]]
+    assert np.array_equal(per_tri[0], np.zeros(9, np.float32))
+    assert np.allclose(per_tri[1], [0.5, 0.5, 0.5, 0.8, 0.1, 0.1, 0.2, 0.2, 0.2])
+    assert np.array_equal(per_tri[2], per_tri[1])
+    assert np.allclose(per_tri[3], [0.4, 0.5, 0.6, 0.1, 0.2, 0.3, 0, 0, 0])  # Kr beyond the 5-line window stays 0
+    assert np.array_equal(a["lights"], np.array([[0, -8, 3, 50, 50, 50], [1, 2, 3, 4, 5, 6]], np.float32))
+    assert np.allclose(a["ambient"], 0.5)
+
+
+def test_loader_errors_do_not_exit(rt, tmp_path):
+    with pytest.raises(rt.RtError) as e:
+        rt.Scene.load_dir(tmp_path / "missing")
+    assert e.value.code == rt.RT_ERR_IO
+    (tmp_path / "triangles.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1/1/1 2/2/2 3/3/3\n")
+    (tmp_path / "triangles.mtl").write_text("")
+    (tmp_path / "lights.obj").write_text("")
+    with pytest.raises(rt.RtError) as e:
+        rt.Scene.load_dir(tmp_path)   # v/vt/vn faces are undefined behaviour in the reference; an error here
+    assert e.value.code == rt.RT_ERR_IO
+
+
+@pytest.mark.parametrize("scene", ["car_only", "car_boxed"])
+def test_obj_loader_equals_reference_loader(rt, scene, scene_arrays):
+    """Our OBJ/MTL/lights parser vs the scene pack dumped from the reference's own triangles_load."""
+    d = O.RefCpu.scene_dir(scene)
+    if not (d / "triangles.obj").exists():
+        pytest.skip("reference assets not staged (oracle/_ref/assets)")
+    a = rt.Scene.load_dir(d).arrays()
+    g = scene_arrays[scene]
+    assert np.array_equal(a["tri"], g["tri"])
+    assert np.array_equal(a["mats"][a["mat_idx"]], g["mats"][g["mat_idx"]])
+    assert np.array_equal(a["lights"], g["lights"])
+
+
+def test_rtsc_roundtrip(rt, tmp_path, scene_arrays):
+    sc = rt.Scene.load_rtsc(GOLD / "scenes" / "soup2k.rtsc")
+    sc.save_rtsc(tmp_path / "x.rtsc")
+    assert (tmp_path / "x.rtsc").read_bytes() == (GOLD / "scenes" / "soup2k.rtsc").read_bytes()
+    (tmp_path / "bad.rtsc").write_bytes(b"RTSC0001" + b"\x00" * 7)
+    with pytest.raises(rt.RtError):
+        rt.Scene.load_rtsc(tmp_path / "bad.rtsc")
+
+
+@pytest.mark.parametrize("scene", SCENES)
+@pytest.mark.parametrize("heuristic", [6, 1, 0])
+def test_bvh_builder_equals_oracle_node_for_node(rt, oracle_scenes, orc, scene_arrays, scene, heuristic):
+    """O(n)-per-node binned builder vs the oracle's literal O(96 n) restatement of bvh_split."""
+    sc = rt.Scene.load_rtsc(GOLD / "scenes" / f"{scene}.rtsc").build_bvh(heuristic)
+    a = sc.arrays()
+    s = oracle_scenes[scene] if heuristic == 6 else orc.scene(scene_arrays[scene])
+    nodes, ti = s.bvh() if heuristic == 6 else s.build_bvh(heuristic)
+    assert np.array_equal(a["bvh_nodes"], nodes)
+    assert np.array_equal(a["tri_idx"], ti)
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_bvh_builder_reproduces_the_reference_binary_tree(rt, manifest, scene):
+    """RT_BVH_REFBIN: digest of bvh[] / tri_idx[] as dumped from the reference CPU binary."""
+    a = rt.Scene.load_rtsc(GOLD / "scenes" / f"{scene}.rtsc").build_bvh(6 | rt.RT_BVH_REFBIN).arrays()
+    m = manifest["scenes"][scene]
+    assert len(a["bvh_nodes"]) // 32 == m["bvh_nodes"]
+    assert sha(a["bvh_nodes"]) == m["bvh_nodes_sha256"]
+    assert sha(a["tri_idx"]) == m["tri_idx_sha256"]
+
+
+def test_bvh_invariants(rt):
+    a = rt.Scene.load_rtsc(GOLD / "scenes" / "car_only.rtsc").build_bvh(6).arrays()
+    dt = np.dtype([("min", "3f4"), ("max", "3f4"), ("len", "i4"), ("idx", "i4")])
+    n = a["bvh_nodes"].view(dt)
+    leaves = n[n["len"] > 0]
+    assert leaves["len"].sum() == len(a["tri"])                       # every triangle in exactly one leaf
+    assert np.array_equal(np.sort(a["tri_idx"]), np.arange(len(a["tri"])))
+    assert leaves["len"].max() <= 2
+    inner = n[(n["len"] == 0) & (n["idx"] != 0)]
+    kids = np.concatenate([inner["idx"], inner["idx"] + 1])
+    assert len(np.unique(kids)) == len(kids) == len(n) - 1            # a tree: every non-root node has one parent
+    tri = a["tri"].reshape(-1, 3, 3)
+    for node in leaves[:200]:
+        t = tri[a["tri_idx"][node["idx"]:node["idx"] + node["len"]]].reshape(-1, 3)
+        assert np.array_equal(t.min(0), node["min"]) and np.array_equal(t.max(0), node["max"])
+
+
+def test_builder_rejects_unsupported(rt):
+    sc = rt.Scene.load_rtsc(GOLD / "scenes" / "soup2k.rtsc")
+    for h in (2, 3, 4, 5, 7):
+        with pytest.raises(rt.RtError):
+            sc.build_bvh(h)
+
+
+def test_soup_generator(rt):
+    a = rt.Scene.soup(500, 1).arrays()
+    t = a["tri"].reshape(-1, 3, 3)
+    assert t.shape[0] == 500 and np.all(t[:, 0] >= -5) and np.all(t[:, 0] <= 5)
+    assert np.all(t[:, 1] - t[:, 0] >= 0) and np.all(t[:, 1] - t[:, 0] <= 1.0001)
+    assert np.array_equal(a["mats"], np.array([[1, 1, 1, 0, 0, 0, 0, 0, 0]], np.float32)) and len(a["lights"]) == 0
+    b = rt.Scene.soup(500, 1).arrays()
+    assert np.array_equal(a["tri"], b["tri"])
+
+
+def test_instance_grid(rt):
+    base = rt.Scene.load_rtsc(GOLD / "scenes" / "soup2k.rtsc")
+    g = base.instance_grid(3, 2, 1, (20.0, 20.0, 20.0), light_every=0).arrays()
+    b = base.arrays()
+    assert g["tri"].shape[0] == 6 * b["tri"].shape[0]
+    assert np.allclose(g["tri"][:2000].reshape(-1, 3, 3)[:, :, 0] + 20.0, b["tri"].reshape(-1, 3, 3)[:, :, 0], atol=1e-5)
+    g2 = base.instance_grid(3, 2, 1, (20.0, 20.0, 20.0)).build_bvh(6).arrays()
+    assert len(g2["bvh_nodes"]) // 32 > 6 * 2000
+
+
+def test_bmp_writer_is_byte_identical_to_the_reference_writer(rt, tmp_path):
+    """Re-encode the pixels of a BMP written by the reference's bmp_write_file (cpu/src/bmp_writer.c)."""
+    ref = (GOLD / "ref_car_only_64x36.bmp").read_bytes()
+    w, h = 64, 36
+    assert len(ref) == 54 + 4 * w * h
+    rows_bottom_up = np.frombuffer(ref, np.uint8, 4 * w * h, 54).reshape(h, w, 4)
+    top_down = rows_bottom_up[::-1].copy()
+    rt.write_bmp(tmp_path / "o.bmp", top_down)
+    assert (tmp_path / "o.bmp").read_bytes() == ref
