@@ -135,6 +135,12 @@ enum { /* rt_render_params.aov_mask */
     RT_AOV_WORK = 8      /* count inner-node visits and triangle tests (slower build of the kernel) */
 };
 
+enum { /* rt_render_params.traversal */
+    RT_TRAVERSAL_DEFAULT = 0,
+    RT_TRAVERSAL_PLAIN = 1,       /* while-while in the reference's visit order */
+    RT_TRAVERSAL_SPECULATIVE = 2  /* postponed leaves: same image, more lanes busy */
+};
+
 enum { /* rt_render_params.gather */
     RT_GATHER_PEER_STORE = 0, /* fused: every device stores finished pixels straight into device 0's frame */
     RT_GATHER_PEER_COPY = 1   /* unfused: local frame, then packed tile copy device->device 0 + unpack */
@@ -157,7 +163,8 @@ typedef struct rt_render_params {
     int32_t   block_threads;    /* threads per CTA */
     int32_t   ctas_per_sm;      /* persistent CTAs per SM */
     int32_t   refill_threshold; /* leave the traversal loop when fewer lanes than this are active */
-    int32_t   reserved[5];
+    int32_t   traversal;        /* RT_TRAVERSAL_* (fast mode only; strict always walks the reference order) */
+    int32_t   reserved[4];
 } rt_render_params;
 
 typedef struct rt_timing {

@@ -164,7 +164,12 @@ static void split(build_t* B, int node_idx, int depth)
 {
     ro_scene* s = B->s;
     node_t* parent = &s->bvh[node_idx];
-    if ((size_t)s->bvh_len >= 2 * (size_t)s->n_tris) return;                          /* :80-83 */
+    if ((size_t)s->bvh_len >= 2 * (size_t)s->n_tris) {                                /* :80-83 */
+        /* the reference returns here without clearing an EMPTY node's union field, which then reads as a
+         * dangling child index (undefined traversal); both this restatement and the product clear it */
+        if (!parent->tr_len) parent->idx = 0;
+        return;
+    }
     if (depth == BVH_MAX_ITER || parent->tr_len <= BVH_ELEMENT_THRESHOLD) {           /* :84 */
         if (!parent->tr_len) parent->idx = 0;                                         /* :85-86 */
         return;

@@ -155,7 +155,12 @@ struct Builder {
     {
         rt_bvh_node* bvh = s.bvh.data();
         rt_bvh_node& parent = bvh[node_idx];
-        if ((size_t)bvh_len >= 2 * n) return;                                     // bvh.c:80-83
+        if ((size_t)bvh_len >= 2 * n) {                                           // bvh.c:80-83
+            // the reference returns without clearing an EMPTY node's union field, which then reads as a
+            // dangling child index; clear it (only reachable with heuristics 0/1 on degenerate input)
+            if (!parent.tr_len) parent.idx = 0;
+            return;
+        }
         if (depth == kMaxDepth || parent.tr_len <= kLeafThreshold) {              // bvh.c:84
             if (!parent.tr_len) parent.idx = 0;                                   // bvh.c:85-86
             return;

@@ -17,12 +17,14 @@
 //           ref == RT_REF_NONE  : empty leaf / nothing (never pushed)
 //           otherwise (ref < 0) : leaf, ~ref = (first_slot << 4) | min(count, 15); count == 15
 //                                 means "look the count up in leaf_cnt[first_slot]"
-//   tris    48 bytes per LEAF-ORDER slot j (slot j holds triangle tri_idx[j], so a leaf's
+//   tris    64 bytes per LEAF-ORDER slot j (slot j holds triangle tri_idx[j], so a leaf's
 //           triangles are contiguous): q0 = (v0.xyz, e1.x) q1 = (e1.yz, e2.xy) q2 = (e2.z, n.xyz)
+//           q3 = (original triangle index as int bits — the first-hit ID space —, 0, 0, 0)
 //           with e1 = v1-v0, e2 = v2-v0, n = e1 x e2 computed in IEEE FP32 on the host in the
 //           reference's operation order (cpu/src/raytracer.c:36-38) — bit-identical to
-//           computing them per test, and never normalised.
-//   tri_orig[j]   original triangle index (the first-hit ID space)
+//           computing them per test, and never normalised.  A test reads the
+//           first 48 bytes (one 256-bit + one 128-bit load); q3 is read once per ray, on a hit.
+//           64-byte records keep every 256-bit load 32-byte aligned.
 //   shade[orig]   (unit normal norm[0].xyz, material index as int bits); norm[1] == -norm[0]
 //   mats    3 x float4 per material: (ks, 0) (kd, 0) (kr, |kr| > 0 ? 1 : 0)
 //   lights  2 x float4 per light: (pos, 0) (kl, 0)
@@ -34,13 +36,12 @@
 
 #define RT_REF_NONE ((int)0x80000000)
 #define RT_LEAF_CNT_ESC 15
-#define RT_STACK_ENTRIES 36   /* reference depth cap 32 (cpu/include/options.h:64) -> at most 33 live entries */
+#define RT_STACK_ENTRIES 40   /* sentinel + reference depth cap 32 (cpu/include/options.h:64) + postponed leaf */
 #define RT_MAX_BOUNCES 8
 
 struct RtDeviceScene {
     const float4* nodes;
     const float4* tris;
-    const int*    tri_orig;
     const float4* shade;
     const float4* mats;
     const float4* lights;

@@ -33,8 +33,7 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
         if (d.tri_idx[j] < 0 || (uint32_t)d.tri_idx[j] >= n) { err = "tri_idx entry out of range"; return RT_ERR_INVALID; }
 
     // ---- triangles in leaf order ----
-    out.tris.resize(12 * (size_t)n);
-    out.tri_orig.resize(n);
+    out.tris.assign(16 * (size_t)n, 0.0f);
     out.shade.resize(4 * (size_t)n);
     for (uint32_t j = 0; j < n; j++) {
         const uint32_t orig = (uint32_t)d.tri_idx[j];
@@ -43,11 +42,11 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
         sub3(c + 3, c, e1);  // raytracer.c:36
         sub3(c + 6, c, e2);  // raytracer.c:37
         cross3(e1, e2, nn);  // raytracer.c:38
-        float* q = &out.tris[12 * (size_t)j];
+        float* q = &out.tris[16 * (size_t)j];
         q[0] = c[0]; q[1] = c[1]; q[2] = c[2]; q[3] = e1[0];
         q[4] = e1[1]; q[5] = e1[2]; q[6] = e2[0]; q[7] = e2[1];
         q[8] = e2[2]; q[9] = nn[0]; q[10] = nn[1]; q[11] = nn[2];
-        out.tri_orig[j] = (int32_t)orig;
+        std::memcpy(&q[12], &orig, 4);
     }
     for (uint32_t i = 0; i < n; i++) {
         const float* c = d.tri_coords + 9 * (size_t)i;
@@ -122,7 +121,7 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
         if (is_inner(d.bvh[b.idx])) st.push_back({(uint32_t)b.idx, it.depth + 1});
     }
     // live stack entries never exceed (inner depth + 2)
-    if (max_depth + 3 > RT_STACK_ENTRIES_HOST) { err = "BVH deeper than the traversal stack (" + std::to_string(max_depth) + ")"; return RT_ERR_INVALID; }
+    if (max_depth + 5 > RT_STACK_ENTRIES_HOST) { err = "BVH deeper than the traversal stack (" + std::to_string(max_depth) + ")"; return RT_ERR_INVALID; }
     out.max_depth = max_depth;
 
     const size_t n_inner = order.empty() ? 1 : order.size();
@@ -139,7 +138,10 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
         // the root itself is a leaf (<= 2 triangles): synthetic inner node, left = root, right = none
         int32_t ref;
         if (!leaf_ref(d.bvh[0], ref)) { err = "BVH leaf range out of bounds"; return RT_ERR_INVALID; }
-        put_child(out.nodes.data(), 0, d.bvh[0], ref);
+        // the reference pops the root untested (cpu/src/bvh.c:321-324): give it a box no ray can miss
+        rt_bvh_node all = d.bvh[0];
+        for (int a = 0; a < 3; a++) { all.min[a] = -1e30f; all.max[a] = 1e30f; }
+        put_child(out.nodes.data(), 0, all, ref);
         put_child(out.nodes.data(), 1, d.bvh[0], RT_REF_NONE_HOST);
     }
     for (size_t k = 0; k < order.size(); k++) {

@@ -9,14 +9,13 @@
 // host mirrors of the device_layout.h constants (that header needs CUDA vector types)
 #define RT_REF_NONE_HOST ((int32_t)0x80000000)
 #define RT_LEAF_CNT_ESC_HOST 15
-#define RT_STACK_ENTRIES_HOST 36
+#define RT_STACK_ENTRIES_HOST 40
 
 namespace rt {
 
 struct FlatScene {
     std::vector<float>   nodes;    // 16 floats (4 x float4) per inner node
-    std::vector<float>   tris;     // 12 floats (3 x float4) per leaf-order slot
-    std::vector<int32_t> tri_orig; // slot -> original triangle index
+    std::vector<float>   tris;     // 16 floats (4 x float4) per leaf-order slot
     std::vector<float>   shade;    // 4 floats per original triangle
     std::vector<float>   mats;     // 12 floats per material
     std::vector<float>   lights;   // 8 floats per light
@@ -27,7 +26,7 @@ struct FlatScene {
 
     size_t bytes() const
     {
-        return 4 * (nodes.size() + tris.size() + tri_orig.size() + shade.size() + mats.size() + lights.size() + leaf_cnt.size());
+        return 4 * (nodes.size() + tris.size() + shade.size() + mats.size() + lights.size() + leaf_cnt.size());
     }
 };
 

@@ -7,6 +7,7 @@ struct RtLaunchCfg {
     int block_threads;  // 128 (default) or 64
     int min_ctas;       // __launch_bounds__ second argument: caps registers/thread
     bool work_counters; // RT_AOV_WORK build (counts inner visits and triangle tests)
+    bool speculative;   // fast build: speculative traversal (postponed leaves)
     int grid;           // number of persistent CTAs
 };
 

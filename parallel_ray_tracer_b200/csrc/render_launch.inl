@@ -5,25 +5,29 @@ namespace RT_KERNEL_NS {
 
 typedef void (*kernel_fn)(const RtDeviceScene, const RtFrameArgs);
 
-template <bool WORK>
+template <bool WORK, bool SPEC>
 static kernel_fn pick(int block, int minb)
 {
     if (block == 64) {
-        if (minb >= 16) return render_kernel<64, 16, WORK>;
-        if (minb >= 12) return render_kernel<64, 12, WORK>;
-        return render_kernel<64, 8, WORK>;
+        if (minb >= 12) return render_kernel<64, 12, WORK, SPEC>;
+        return render_kernel<64, 8, WORK, SPEC>;
     }
-    if (minb >= 8) return render_kernel<128, 8, WORK>;
-    if (minb >= 6) return render_kernel<128, 6, WORK>;
-    if (minb >= 5) return render_kernel<128, 5, WORK>;
-    if (minb >= 4) return render_kernel<128, 4, WORK>;
-    if (minb >= 3) return render_kernel<128, 3, WORK>;
-    return render_kernel<128, 2, WORK>;
+    if (minb >= 8) return render_kernel<128, 8, WORK, SPEC>;
+    if (minb >= 6) return render_kernel<128, 6, WORK, SPEC>;
+    if (minb >= 5) return render_kernel<128, 5, WORK, SPEC>;
+    if (minb >= 4) return render_kernel<128, 4, WORK, SPEC>;
+    return render_kernel<128, 3, WORK, SPEC>;
 }
 
 static kernel_fn pick(const RtLaunchCfg& c)
 {
-    return c.work_counters ? pick<true>(c.block_threads, c.min_ctas) : pick<false>(c.block_threads, c.min_ctas);
+#if RT_STRICT
+    // the strict build never speculates: its visit order is the reference's, node for node
+    return c.work_counters ? pick<true, false>(c.block_threads, c.min_ctas) : pick<false, false>(c.block_threads, c.min_ctas);
+#else
+    if (c.speculative) return c.work_counters ? pick<true, true>(c.block_threads, c.min_ctas) : pick<false, true>(c.block_threads, c.min_ctas);
+    return c.work_counters ? pick<true, false>(c.block_threads, c.min_ctas) : pick<false, false>(c.block_threads, c.min_ctas);
+#endif
 }
 
 static cudaError_t launch(const RtDeviceScene& sc, const RtFrameArgs& fa, const RtLaunchCfg& cfg, cudaStream_t st)

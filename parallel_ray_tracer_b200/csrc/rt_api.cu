@@ -28,7 +28,7 @@ struct Dev {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     // scene (replicated per device)
     float4 *nodes = nullptr, *tris = nullptr, *shade = nullptr, *mats = nullptr, *lights = nullptr;
-    int *tri_orig = nullptr, *leaf_cnt = nullptr;
+    int* leaf_cnt = nullptr;
     // per-frame control block: [0..3] stats (u64), then the tile counter
     unsigned long long* ctrl = nullptr;
     unsigned long long* ctrl_host = nullptr; // pinned
@@ -200,7 +200,7 @@ void free_dev(Dev& D)
 {
     cudaSetDevice(D.id);
     cudaFree(D.nodes); cudaFree(D.tris); cudaFree(D.shade); cudaFree(D.mats); cudaFree(D.lights);
-    cudaFree(D.tri_orig); cudaFree(D.leaf_cnt); cudaFree(D.ctrl); cudaFree(D.tile_list);
+    cudaFree(D.leaf_cnt); cudaFree(D.ctrl); cudaFree(D.tile_list);
     cudaFree(D.bgra); cudaFree(D.packed); cudaFree(D.rgb); cudaFree(D.tri_id); cudaFree(D.depth);
     if (D.ctrl_host) cudaFreeHost(D.ctrl_host);
     if (D.ev0) cudaEventDestroy(D.ev0);
@@ -284,7 +284,6 @@ int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** 
         CKC(cudaEventCreate(&D.ev0)); CKC(cudaEventCreate(&D.ev1)); CKC(cudaEventCreate(&D.ev2));
         CKC(upload(&D.nodes, flat.nodes.data(), flat.nodes.size() * 4, D.stream));
         CKC(upload(&D.tris, flat.tris.data(), flat.tris.size() * 4, D.stream));
-        CKC(upload(&D.tri_orig, flat.tri_orig.data(), flat.tri_orig.size() * 4, D.stream));
         CKC(upload(&D.shade, flat.shade.data(), flat.shade.size() * 4, D.stream));
         CKC(upload(&D.mats, flat.mats.data(), flat.mats.size() * 4, D.stream));
         CKC(upload(&D.lights, flat.lights.data(), flat.lights.size() * 4, D.stream));
@@ -371,6 +370,7 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
     cfg.block_threads = p->block_threads == 64 ? 64 : 128;
     cfg.min_ctas = p->ctas_per_sm > 0 ? p->ctas_per_sm : (cfg.block_threads == 64 ? 8 : 4);
     cfg.work_counters = (p->aov_mask & RT_AOV_WORK) != 0;
+    cfg.speculative = p->traversal != RT_TRAVERSAL_PLAIN;
     fa.refill_threshold = p->refill_threshold > 0 ? std::min(p->refill_threshold, 32) : 20;
 
     unsigned launches = 0;
@@ -395,7 +395,7 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
         Dev& D = c->devs[d];
         CK(c, cudaSetDevice(D.id));
         RtDeviceScene sc = c->scene_host_view;
-        sc.nodes = D.nodes; sc.tris = D.tris; sc.tri_orig = D.tri_orig; sc.shade = D.shade;
+        sc.nodes = D.nodes; sc.tris = D.tris; sc.shade = D.shade;
         sc.mats = D.mats; sc.lights = D.lights; sc.leaf_cnt = D.leaf_cnt;
         RtFrameArgs f = fa;
         f.tile_list = D.tile_list; f.n_tiles = D.n_tiles;
@@ -412,7 +412,7 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
         if (occ < 1) return fail(c, RT_ERR_CUDA, "rt_render: kernel does not fit on an SM");
         RtLaunchCfg cf = cfg;
         cf.grid = D.sm_count * occ; // persistent: exactly one resident wave
-        const int warps_needed = (D.n_tiles * RT_TILE_PIXELS / 32 + (cf.block_threads / 32) - 1) / (cf.block_threads / 32);
+        const int warps_needed = (D.n_tiles * (RT_TILE_PIXELS / 32) + (cf.block_threads / 32) - 1) / (cf.block_threads / 32);
         if (warps_needed < cf.grid) cf.grid = std::max(warps_needed, 1);
 
         CK(c, cudaMemsetAsync(D.ctrl, 0, 64, D.stream));

@@ -105,7 +105,7 @@ def test_spp_strict_bit_exact_and_golden(rt, gpu_scenes, oracle_scenes, spp):
 def test_bounce_limits(rt, gpu_scenes, oracle_scenes, bounces):
     w, h = 200, 112
     ref = oracle_scenes["car_boxed"].render(w, h, bounces=bounces)
-    got = render(rt, gpu_scenes["car_boxed"][1], w, h, rt.RT_MODE_STRICT, bounces=bounces, aov_mask=1)
+    got = render(rt, gpu_scenes["car_boxed"][1], w, h, rt.RT_MODE_STRICT, bounces=bounces)
     assert np.array_equal(got["bgra"], ref["bgra"])
     if bounces == 0:
         assert np.all(got["bgra"][..., :3] == 0) and np.all(got["bgra"][..., 3] == 255)
@@ -151,7 +151,8 @@ def test_degenerate_scenes(rt, orc):
 
 
 def test_deep_leaf_with_many_triangles(rt, orc):
-    """Heuristic 0 on a soup hits the depth-32 cap and leaves big leaves (count escape path)."""
+    """Heuristic 0 on a soup hits the depth-32 cap (and the reference's 2N node guard) and leaves big
+    leaves: exercises the leaf-count escape path."""
     sc = rt.Scene.load_rtsc(O.HERE.parent / "tests" / "golden" / "scenes" / "soup2k.rtsc").build_bvh(0)
     a = sc.arrays()
     dt = np.dtype([("min", "3f4"), ("max", "3f4"), ("len", "i4"), ("idx", "i4")])
