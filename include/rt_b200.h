@@ -141,6 +141,12 @@ enum { /* rt_render_params.traversal */
     RT_TRAVERSAL_SPECULATIVE = 2  /* postponed leaves: same image, more lanes busy */
 };
 
+enum { /* rt_render_params.tile_feedback */
+    RT_FEEDBACK_DEFAULT = 0, /* on */
+    RT_FEEDBACK_ON = 1,
+    RT_FEEDBACK_OFF = 2      /* row-major tile order every frame */
+};
+
 enum { /* rt_render_params.gather */
     RT_GATHER_PEER_STORE = 0, /* fused: every device stores finished pixels straight into device 0's frame */
     RT_GATHER_PEER_COPY = 1   /* unfused: local frame, then packed tile copy device->device 0 + unpack */
@@ -164,7 +170,8 @@ typedef struct rt_render_params {
     int32_t   ctas_per_sm;      /* persistent CTAs per SM */
     int32_t   refill_threshold; /* leave the traversal loop when fewer lanes than this are active */
     int32_t   traversal;        /* RT_TRAVERSAL_* (fast mode only; strict always walks the reference order) */
-    int32_t   reserved[4];
+    int32_t   tile_feedback;    /* RT_FEEDBACK_*: order each frame's tiles by the cost measured in the previous frame */
+    int32_t   reserved[3];
 } rt_render_params;
 
 typedef struct rt_timing {
@@ -217,6 +224,8 @@ int rt_unpack_tiles(rt_ctx* ctx, const void* dev_gathered, size_t stride_bytes, 
  * process's frame the peer-store target of this context's renders. */
 int rt_frame_ipc_export(rt_ctx* ctx, int width, int height, void* handle64);
 int rt_frame_ipc_import(rt_ctx* ctx, const void* handle64, int width, int height);
+/* Diagnostics: per-warp timeline of RT_AOV_WORK renders (8 x u64 per warp, see csrc/rt_api.cu). */
+int rt_debug_warp_trace(rt_ctx* ctx, int enable, unsigned long long* out, int max_warps);
 /* Raw device pointer of the BGRA frame (device 0 of the context). */
 int rt_frame_device_ptr(rt_ctx* ctx, void** dev_ptr, size_t* bytes);
 

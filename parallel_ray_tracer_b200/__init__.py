@@ -32,6 +32,7 @@ RT_AOV_RGB_F32, RT_AOV_TRI_ID, RT_AOV_DEPTH, RT_AOV_WORK = 1, 2, 4, 8
 RT_GATHER_PEER_STORE, RT_GATHER_PEER_COPY = 0, 1
 RT_BVH_REFBIN = 0x100
 RT_TRAVERSAL_DEFAULT, RT_TRAVERSAL_PLAIN, RT_TRAVERSAL_SPECULATIVE = 0, 1, 2
+RT_FEEDBACK_DEFAULT, RT_FEEDBACK_ON, RT_FEEDBACK_OFF = 0, 1, 2
 RT_TILE_W, RT_TILE_H = 16, 8
 RT_MAX_DEVICES = 16
 
@@ -41,7 +42,7 @@ EXPORTS = [
     "rt_scene_soup", "rt_scene_instance_grid", "rt_scene_build_bvh", "rt_scene_view", "rt_scene_free",
     "rt_render_params_default", "rt_create", "rt_render", "rt_download", "rt_destroy", "rt_last_error",
     "rt_part_tile_count", "rt_packed_tiles", "rt_unpack_tiles", "rt_frame_ipc_export", "rt_frame_ipc_import",
-    "rt_frame_device_ptr", "rt_write_bmp", "rt_abi_version", "rt_device_count",
+    "rt_frame_device_ptr", "rt_write_bmp", "rt_abi_version", "rt_device_count", "rt_debug_warp_trace",
 ]
 
 
@@ -70,7 +71,7 @@ class rt_render_params(C.Structure):
                 ("seed", C.c_uint32), ("bounces", C.c_int32), ("mode", C.c_int32), ("aov_mask", C.c_int32),
                 ("gather", C.c_int32), ("part_index", C.c_int32), ("part_count", C.c_int32),
                 ("block_threads", C.c_int32), ("ctas_per_sm", C.c_int32), ("refill_threshold", C.c_int32),
-                ("traversal", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("traversal", C.c_int32), ("tile_feedback", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class rt_timing(C.Structure):
@@ -125,6 +126,7 @@ def lib() -> C.CDLL:
     L.rt_frame_ipc_import.argtypes = [vp, vp, i32, i32]
     L.rt_frame_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.rt_write_bmp.argtypes = [C.c_char_p, vp, i32, i32]
+    L.rt_debug_warp_trace.argtypes = [vp, i32, vp, i32]
     _lib = L
     return L
 
@@ -320,6 +322,12 @@ class Context:
     def frame_ipc_import(self, handle: bytes, width, height):
         buf = C.create_string_buffer(handle, 64)
         _check(lib().rt_frame_ipc_import(self._h, buf, width, height), self._h)
+
+    def warp_trace(self, enable=True, max_warps=8192):
+        """Diagnostics: arm / read the per-warp timeline of RT_AOV_WORK renders (see rt_debug_warp_trace)."""
+        buf = np.zeros((max_warps, 8), np.uint64)
+        n = lib().rt_debug_warp_trace(self._h, int(enable), _ptr(buf), max_warps)
+        return buf[:max(n, 0)]
 
     def close(self):
         if self._h:

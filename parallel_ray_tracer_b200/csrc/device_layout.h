@@ -59,6 +59,7 @@ struct RtFrameArgs {
     const unsigned* tile_list;     // tiles this device renders (tile id = ty * tiles_x + tx)
     int   n_tiles;
     unsigned* tile_counter;        // persistent-CTA work counter (device-local)
+    unsigned* tile_cost;           // optional: per-tile traversal-iteration count of this frame (scheduling feedback)
     int   refill_threshold;
     // outputs (bgra may be a peer-mapped pointer into device 0's frame)
     uchar4* bgra;
@@ -66,4 +67,5 @@ struct RtFrameArgs {
     int*    tri_id;                // optional
     float*  depth;                 // optional
     unsigned long long* stats;     // [0] closest rays [1] shadow rays [2] inner visits [3] triangle tests
+    unsigned long long* warp_trace; // optional, RT_AOV_WORK builds: 8 x u64 per warp (clock64 start / queue empty / exit, counts)
 };

@@ -128,7 +128,10 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
     out.nodes.assign(16 * n_inner, 0.0f);
     auto put_child = [&](float* q, int which, const rt_bvh_node& c, int32_t ref) {
         float mn[3], mx[3];
-        if (ref == RT_REF_NONE_HOST) { for (int a = 0; a < 3; a++) { mn[a] = 1e30f; mx[a] = -1e30f; } } // never hit
+        // An empty child must never be entered.  The slab test cannot see an inverted box (it takes min/max of
+        // the two plane distances), so use a degenerate box at +infinity: every plane distance is +-inf, hence
+        // either tmax < 0 (miss) or tmin = +inf, which is never < t.
+        if (ref == RT_REF_NONE_HOST) { for (int a = 0; a < 3; a++) { mn[a] = INFINITY; mx[a] = INFINITY; } }
         else { std::memcpy(mn, c.min, 12); std::memcpy(mx, c.max, 12); }
         if (which == 0) { q[0] = mn[0]; q[1] = mn[1]; q[2] = mn[2]; q[3] = mx[0]; q[4] = mx[1]; q[5] = mx[2]; }
         else { q[6] = mn[0]; q[7] = mn[1]; q[8] = mn[2]; q[9] = mx[0]; q[10] = mx[1]; q[11] = mx[2]; }

@@ -19,11 +19,12 @@ def main():
         sc = rt.Scene.load_rtsc(ROOT / "tests" / "golden" / "scenes" / f"{scene}.rtsc").build_bvh(6)
         ctx = rt.Context(sc, [0])
         for mode in (rt.RT_MODE_FAST, rt.RT_MODE_STRICT):
-            grid = [(128, c, r, t) for c in (4, 6) for r in (8, 12, 16, 20, 24, 28) for t in (1, 2)] + [(64, 12, r, t) for r in (16, 24) for t in (1, 2)]
+            grid = [(128, c, r, t, f) for c in (4, 6) for r in (12, 20, 28) for t in (1, 2) for f in (1, 2)]
             if mode == rt.RT_MODE_STRICT:
-                grid = [(128, 4, 20, 1), (128, 5, 24, 1)]
-            for block, ctas, refill, trav in grid:
-                p = rt.default_params(width=w, height=h, mode=mode, block_threads=block, ctas_per_sm=ctas, refill_threshold=refill, traversal=trav)
+                grid = [(128, 5, 24, 1, 1), (128, 5, 24, 1, 2)]
+            for block, ctas, refill, trav, fb in grid:
+                p = rt.default_params(width=w, height=h, mode=mode, block_threads=block, ctas_per_sm=ctas, refill_threshold=refill, traversal=trav,
+                                      tile_feedback=fb)
                 ms = []
                 for i in range(frames + 3):
                     tm = ctx.render_frame(p)
@@ -32,7 +33,7 @@ def main():
                 rays = tm.rays_closest + tm.rays_shadow
                 med = statistics.median(ms)
                 print(json.dumps({"scene": scene, "w": w, "h": h, "mode": "strict" if mode else "fast", "block": block, "ctas_per_sm": ctas,
-                                  "refill": refill, "traversal": trav, "kernel_ms_median": round(med, 4), "kernel_ms_min": round(min(ms), 4),
+                                  "refill": refill, "traversal": trav, "feedback": fb, "kernel_ms_median": round(med, 4), "kernel_ms_min": round(min(ms), 4),
                                   "mrays_s": round(rays / med / 1e3, 1), "rays": rays}), flush=True)
         ctx.close()
 
