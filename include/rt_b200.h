@@ -141,12 +141,6 @@ enum { /* rt_render_params.traversal */
     RT_TRAVERSAL_SPECULATIVE = 2  /* postponed leaves: same image, more lanes busy */
 };
 
-enum { /* rt_render_params.tile_feedback */
-    RT_FEEDBACK_DEFAULT = 0, /* on */
-    RT_FEEDBACK_ON = 1,
-    RT_FEEDBACK_OFF = 2      /* row-major tile order every frame */
-};
-
 enum { /* rt_render_params.gather */
     RT_GATHER_PEER_STORE = 0, /* fused: every device stores finished pixels straight into device 0's frame */
     RT_GATHER_PEER_COPY = 1   /* unfused: local frame, then packed tile copy device->device 0 + unpack */
@@ -170,8 +164,7 @@ typedef struct rt_render_params {
     int32_t   ctas_per_sm;      /* persistent CTAs per SM */
     int32_t   refill_threshold; /* leave the traversal loop when fewer lanes than this are active */
     int32_t   traversal;        /* RT_TRAVERSAL_* (fast mode only; strict always walks the reference order) */
-    int32_t   tile_feedback;    /* RT_FEEDBACK_*: order each frame's tiles by the cost measured in the previous frame */
-    int32_t   reserved[3];
+    int32_t   reserved[4];
 } rt_render_params;
 
 typedef struct rt_timing {

@@ -32,7 +32,6 @@ RT_AOV_RGB_F32, RT_AOV_TRI_ID, RT_AOV_DEPTH, RT_AOV_WORK = 1, 2, 4, 8
 RT_GATHER_PEER_STORE, RT_GATHER_PEER_COPY = 0, 1
 RT_BVH_REFBIN = 0x100
 RT_TRAVERSAL_DEFAULT, RT_TRAVERSAL_PLAIN, RT_TRAVERSAL_SPECULATIVE = 0, 1, 2
-RT_FEEDBACK_DEFAULT, RT_FEEDBACK_ON, RT_FEEDBACK_OFF = 0, 1, 2
 RT_TILE_W, RT_TILE_H = 16, 8
 RT_MAX_DEVICES = 16
 
@@ -71,7 +70,7 @@ class rt_render_params(C.Structure):
                 ("seed", C.c_uint32), ("bounces", C.c_int32), ("mode", C.c_int32), ("aov_mask", C.c_int32),
                 ("gather", C.c_int32), ("part_index", C.c_int32), ("part_count", C.c_int32),
                 ("block_threads", C.c_int32), ("ctas_per_sm", C.c_int32), ("refill_threshold", C.c_int32),
-                ("traversal", C.c_int32), ("tile_feedback", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("traversal", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class rt_timing(C.Structure):

@@ -59,7 +59,6 @@ struct RtFrameArgs {
     const unsigned* tile_list;     // tiles this device renders (tile id = ty * tiles_x + tx)
     int   n_tiles;
     unsigned* tile_counter;        // persistent-CTA work counter (device-local)
-    unsigned* tile_cost;           // optional: per-tile traversal-iteration count of this frame (scheduling feedback)
     int   refill_threshold;
     // outputs (bgra may be a peer-mapped pointer into device 0's frame)
     uchar4* bgra;

@@ -9,6 +9,7 @@ template <bool WORK, bool SPEC>
 static kernel_fn pick(int block, int minb)
 {
     if (block == 64) {
+        if (minb >= 16) return render_kernel<64, 16, WORK, SPEC>;
         if (minb >= 12) return render_kernel<64, 12, WORK, SPEC>;
         return render_kernel<64, 8, WORK, SPEC>;
     }

