@@ -12,18 +12,29 @@ sys.path.insert(0, str(ROOT))
 import parallel_ray_tracer_b200 as rt  # noqa: E402
 
 
+def clocks():
+    import subprocess
+    try:
+        return subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active", "--format=csv,noheader"],
+                              capture_output=True, text=True, timeout=20).stdout.strip()
+    except Exception as e:
+        return str(e)
+
+
 def main():
+    print(json.dumps({"clocks_idle": clocks()}), flush=True)
     frames = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     cases = [("car_only", 1920, 1080), ("car_boxed", 1920, 1080), ("car_boxed", 3840, 2160)]
     for scene, w, h in cases:
         sc = rt.Scene.load_rtsc(ROOT / "tests" / "golden" / "scenes" / f"{scene}.rtsc").build_bvh(6)
         ctx = rt.Context(sc, [0])
         for mode in (rt.RT_MODE_STRICT, rt.RT_MODE_FAST):
-            grid = [(b, c, r, 2, f) for rep in (0, 1) for f in (2, 1) for (b, c) in ((128, 6), (128, 4)) for r in (16, 20)]
+            grid = [(b, c, r, 2, f) for rep in (0, 1) for f in (0,) for (b, c) in ((128, 6), (128, 4), (64, 12)) for r in (16, 20)]
             if mode == rt.RT_MODE_STRICT:
-                grid = [(128, 5, 24, 1, 2), (128, 5, 24, 1, 1), (128, 5, 24, 1, 2), (128, 5, 24, 1, 1)]
+                grid = [(128, 5, 24, 1, 2), (128, 5, 24, 1, 2)]
             for block, ctas, refill, trav, fb in grid:
                 p = rt.default_params(width=w, height=h, mode=mode, block_threads=block, ctas_per_sm=ctas, refill_threshold=refill, traversal=trav)
+                p.reserved[0] = fb
                 ms = []
                 import time
                 t_end = time.perf_counter() + 0.15   # >= 150 ms of warm-up per configuration (clock ramp)
@@ -34,8 +45,8 @@ def main():
                     ms.append(tm.kernel_ms[0])
                 rays = tm.rays_closest + tm.rays_shadow
                 med = statistics.median(ms)
-                print(json.dumps({"scene": scene, "w": w, "h": h, "mode": "strict" if mode else "fast", "block": block, "ctas_per_sm": ctas,
-                                  "refill": refill, "traversal": trav, "feedback": fb, "kernel_ms_median": round(med, 4), "kernel_ms_min": round(min(ms), 4),
+                print(json.dumps({"clocks": clocks(), "scene": scene, "w": w, "h": h, "mode": "strict" if mode else "fast", "block": block, "ctas_per_sm": ctas,
+                                  "refill": refill, "traversal": trav, "stack": fb, "kernel_ms_median": round(med, 4), "kernel_ms_min": round(min(ms), 4),
                                   "mrays_s": round(rays / med / 1e3, 1), "rays": rays}), flush=True)
         ctx.close()
 
