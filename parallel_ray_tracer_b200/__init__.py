@@ -24,7 +24,7 @@ from pathlib import Path
 import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "librt_b200.so"
+LIB_PATH = Path(os.environ.get("RT_B200_LIB", PKG_DIR / "librt_b200.so"))  # override: A/B runs of two builds
 
 RT_OK, RT_ERR_INVALID, RT_ERR_IO, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_NOMEM, RT_ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 RT_MODE_FAST, RT_MODE_STRICT = 0, 1

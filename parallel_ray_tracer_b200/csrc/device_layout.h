@@ -33,6 +33,8 @@
 #include "rt_b200.h"
 
 #define RT_TILE_PIXELS (RT_TILE_W * RT_TILE_H)
+#define RT_MACRO_CHUNKS 16u /* chunks (8x4 pixels) per macro tile = 4 tiles */
+#define RT_MAX_SMS 256
 
 #define RT_REF_NONE ((int)0x80000000)
 #define RT_LEAF_CNT_ESC 15
@@ -59,6 +61,8 @@ struct RtFrameArgs {
     const unsigned* tile_list;     // tiles this device renders (tile id = ty * tiles_x + tx)
     int   n_tiles;
     unsigned* tile_counter;        // persistent-CTA work counter (device-local)
+    unsigned long long* sm_cursor; // RT_OPT_SMQUEUE: one work cursor per SM (indexed by %smid), zeroed per frame
+    unsigned n_sms;
     int   refill_threshold;
     // outputs (bgra may be a peer-mapped pointer into device 0's frame)
     uchar4* bgra;

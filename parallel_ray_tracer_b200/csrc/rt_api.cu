@@ -145,13 +145,17 @@ __global__ void unpack_tiles_kernel(uchar4* __restrict__ frame, const uchar4* __
 inline int tiles_x_of(int w) { return (w + RT_TILE_W - 1) / RT_TILE_W; }
 inline int tiles_y_of(int h) { return (h + RT_TILE_H - 1) / RT_TILE_H; }
 
+// Tiles of one part in rendering order: 2x2 blocks of tiles (32x16 pixels) in raster order, so that consecutive
+// list entries are spatial neighbours.  The same order defines the layout of packed tile buffers.
 void make_tile_list(int w, int h, int part, int parts, std::vector<unsigned>& out)
 {
     out.clear();
     const int tx_n = tiles_x_of(w), ty_n = tiles_y_of(h);
-    for (int ty = 0; ty < ty_n; ty++)
-        for (int tx = 0; tx < tx_n; tx++)
-            if (rt_tile_owner(tx, ty, parts) == part) out.push_back((unsigned)(ty * tx_n + tx));
+    for (int by = 0; by < ty_n; by += 2)
+        for (int bx = 0; bx < tx_n; bx += 2)
+            for (int ty = by; ty < std::min(by + 2, ty_n); ty++)
+                for (int tx = bx; tx < std::min(bx + 2, tx_n); tx++)
+                    if (rt_tile_owner(tx, ty, parts) == part) out.push_back((unsigned)(ty * tx_n + tx));
 }
 
 template <class T>
@@ -190,9 +194,11 @@ int setup_local_index(rt_ctx* c, int w, int h, int parts)
 {
     if (c->li_w == w && c->li_h == h && c->li_parts == parts && c->local_index) return RT_OK;
     const int tx_n = tiles_x_of(w), ty_n = tiles_y_of(h);
-    std::vector<unsigned> li((size_t)tx_n * ty_n), next((size_t)parts, 0u);
-    for (int ty = 0; ty < ty_n; ty++)
-        for (int tx = 0; tx < tx_n; tx++) li[(size_t)ty * tx_n + tx] = next[rt_tile_owner(tx, ty, parts)]++;
+    std::vector<unsigned> li((size_t)tx_n * ty_n), tl;
+    for (int p = 0; p < parts; p++) {
+        make_tile_list(w, h, p, parts, tl);
+        for (size_t i = 0; i < tl.size(); i++) li[tl[i]] = (unsigned)i;
+    }
     Dev& D0 = c->devs[0];
     CK(c, cudaSetDevice(D0.id));
     int rc = ensure(c, &c->local_index, &c->local_index_cap, li.size());
@@ -295,7 +301,7 @@ int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** 
         CKC(upload(&D.mats, flat.mats.data(), flat.mats.size() * 4, D.stream));
         CKC(upload(&D.lights, flat.lights.data(), flat.lights.size() * 4, D.stream));
         CKC(upload(&D.leaf_cnt, flat.leaf_cnt.data(), flat.leaf_cnt.size() * 4, D.stream));
-        CKC(cudaMalloc((void**)&D.ctrl, 64));
+        CKC(cudaMalloc((void**)&D.ctrl, 64 + 8 * RT_MAX_SMS));
         CKC(cudaMallocHost((void**)&D.ctrl_host, 64));
         CKC(cudaStreamSynchronize(D.stream));
         if (i > 0) { // NVLink / NVSwitch peer mapping towards the frame owner
@@ -407,6 +413,8 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
         RtFrameArgs f = fa;
         f.tile_list = D.tile_list; f.n_tiles = D.n_tiles;
         f.stats = D.ctrl; f.tile_counter = reinterpret_cast<unsigned*>(D.ctrl + 4);
+        f.sm_cursor = D.ctrl + 8;
+        f.n_sms = (unsigned)std::min(D.sm_count, RT_MAX_SMS);
         const bool local = (d > 0 && gather == RT_GATHER_PEER_COPY);
         f.bgra = local ? D.bgra : (c->ipc_frame ? c->ipc_frame : D0.bgra); // peer-mapped for d > 0
         f.rgb = (p->aov_mask & RT_AOV_RGB_F32) ? D0.rgb : nullptr;
@@ -432,7 +440,7 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
             f.warp_trace = D.warp_trace;
             D.warp_trace_n = (int)nw;
         }
-        CK(c, cudaMemsetAsync(D.ctrl, 0, 64, D.stream));
+        CK(c, cudaMemsetAsync(D.ctrl, 0, 64 + 8 * RT_MAX_SMS, D.stream));
         CK(c, cudaEventRecord(D.ev0, D.stream));
         e = (p->mode == RT_MODE_STRICT) ? rt_launch_strict(sc, f, cf, D.stream) : rt_launch_fast(sc, f, cf, D.stream);
         CK(c, e);

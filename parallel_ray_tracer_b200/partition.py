@@ -23,10 +23,14 @@ def tile_owner(tx, ty, parts: int):
 
 
 def part_tiles(width: int, height: int, part: int, parts: int) -> np.ndarray:
-    """Tile ids (ty * tiles_x + tx) owned by `part`, in the order the kernel's tile list has them."""
+    """Tile ids (ty * tiles_x + tx) owned by `part`, in the order the kernel's tile list has them: 2x2 blocks of
+    tiles in raster order (make_tile_list in csrc/rt_api.cu)."""
     nx, ny = tiles_xy(width, height)
     ty, tx = np.divmod(np.arange(nx * ny), nx)
-    return np.flatnonzero(tile_owner(tx, ty, parts) == part).astype(np.uint32)
+    ids = np.flatnonzero(tile_owner(tx, ty, parts) == part)
+    ty, tx = ty[ids], tx[ids]
+    key = ((ty // 2) * ((nx + 1) // 2) + tx // 2) * 4 + (ty % 2) * 2 + (tx % 2)
+    return ids[np.argsort(key, kind="stable")].astype(np.uint32)
 
 
 def pack(frame: np.ndarray, part: int, parts: int) -> np.ndarray:
