@@ -95,6 +95,24 @@ def test_bvh_builder_reproduces_the_reference_binary_tree(rt, manifest, scene):
     assert sha(a["tri_idx"]) == m["tri_idx_sha256"]
 
 
+def test_parallel_build_equals_serial_build(rt, monkeypatch):
+    """>= 200 000 triangles take the parallel path (subtrees built concurrently, reference numbering assigned
+    afterwards): the arrays must equal the serial build's, node for node."""
+    base = rt.Scene.load_rtsc(GOLD / "scenes" / "car_only.rtsc")
+    big = base.instance_grid(3, 3, 1, (11.0, 6.5, 3.0))
+    monkeypatch.setenv("RT_BVH_THREADS", "1")
+    a = big.build_bvh(6).arrays()
+    monkeypatch.setenv("RT_BVH_THREADS", "6")
+    b = big.build_bvh(6).arrays()
+    assert len(a["tri"]) == 9 * 32136 and len(a["bvh_nodes"]) // 32 > 300000
+    assert np.array_equal(a["bvh_nodes"], b["bvh_nodes"]) and np.array_equal(a["tri_idx"], b["tri_idx"])
+    monkeypatch.setenv("RT_BVH_THREADS", "3")
+    c = big.build_bvh(6 | rt.RT_BVH_REFBIN).arrays()
+    monkeypatch.setenv("RT_BVH_THREADS", "1")
+    d = big.build_bvh(6 | rt.RT_BVH_REFBIN).arrays()
+    assert np.array_equal(c["bvh_nodes"], d["bvh_nodes"]) and np.array_equal(c["tri_idx"], d["tri_idx"])
+
+
 def test_bvh_invariants(rt):
     a = rt.Scene.load_rtsc(GOLD / "scenes" / "car_only.rtsc").build_bvh(6).arrays()
     dt = np.dtype([("min", "3f4"), ("max", "3f4"), ("len", "i4"), ("idx", "i4")])
