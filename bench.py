@@ -306,7 +306,8 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
     launches = int(allsum(launches))
 
     # ---- work counters (separate, untimed pass with the counting build) for the roofline ----
-    pw = rt.default_params(**base, aov_mask=rt.RT_AOV_WORK)
+    # (strict build: it walks the reference's visit order, so the counts are the algorithmic work of SURVEY §8d)
+    pw = rt.default_params(**base, aov_mask=rt.RT_AOV_WORK, mode=rt.RT_MODE_STRICT)
     tmw = ctx.render_frame(pw)
     inner = int(allsum(tmw.inner_visits)); tris = int(allsum(tmw.tri_tests))
 
@@ -352,7 +353,8 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
                                     "L1/L2 resident, so this is not an HBM-bound kernel (frac > 1 is cache reuse); see roofline_fp32"},
                "roofline_fp32": {"achieved_tlaneops": fp_ach, "peak_tlaneops": fp_peak, "frac": fp_ach / fp_peak,
                                  "note": "48 flops x inner visits + 54 x triangle tests vs 148 SM x 128 lanes x max SM clock"},
-               "work": {"inner_visits": inner, "tri_tests": tris}}
+               "work": {"inner_visits": inner, "tri_tests": tris,
+                        "note": "reference visit order (strict build counters == oracle counters, tests/test_gpu_parity.py)"}}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

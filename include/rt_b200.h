@@ -138,7 +138,8 @@ enum { /* rt_render_params.aov_mask */
 enum { /* rt_render_params.traversal */
     RT_TRAVERSAL_DEFAULT = 0,
     RT_TRAVERSAL_PLAIN = 1,       /* while-while in the reference's visit order */
-    RT_TRAVERSAL_SPECULATIVE = 2  /* postponed leaves: same image, more lanes busy */
+    RT_TRAVERSAL_SPECULATIVE = 2, /* 2-wide tree, postponed leaves: same image, more lanes busy */
+    RT_TRAVERSAL_WIDE = 3         /* 4-wide collapse of the reference tree + postponed leaves (default when it fits) */
 };
 
 enum { /* rt_render_params.gather */

@@ -31,7 +31,7 @@ RT_MODE_FAST, RT_MODE_STRICT = 0, 1
 RT_AOV_RGB_F32, RT_AOV_TRI_ID, RT_AOV_DEPTH, RT_AOV_WORK = 1, 2, 4, 8
 RT_GATHER_PEER_STORE, RT_GATHER_PEER_COPY = 0, 1
 RT_BVH_REFBIN = 0x100
-RT_TRAVERSAL_DEFAULT, RT_TRAVERSAL_PLAIN, RT_TRAVERSAL_SPECULATIVE = 0, 1, 2
+RT_TRAVERSAL_DEFAULT, RT_TRAVERSAL_PLAIN, RT_TRAVERSAL_SPECULATIVE, RT_TRAVERSAL_WIDE = 0, 1, 2, 3
 RT_TILE_W, RT_TILE_H = 16, 8
 RT_MAX_DEVICES = 16
 

@@ -39,10 +39,12 @@
 #define RT_REF_NONE ((int)0x80000000)
 #define RT_LEAF_CNT_ESC 15
 #define RT_STACK_ENTRIES 40   /* sentinel + reference depth cap 32 (cpu/include/options.h:64) + postponed leaf */
+#define RT_STACK_ENTRIES_WIDE 48 /* 4-wide tree: up to three siblings stay pushed per level */
 #define RT_MAX_BOUNCES 8
 
 struct RtDeviceScene {
     const float4* nodes;
+    const float4* nodes4;   // 4-wide collapse (fast build), 8 x float4 per node
     const float4* tris;
     const float4* shade;
     const float4* mats;

@@ -3,6 +3,7 @@
 // All derived quantities (edges, face normal, unit normal, |kr| > 0) are computed here in IEEE
 // FP32 in the reference's operation order, so the strict kernel sees the bits the oracle computes.
 // Must be compiled with -ffp-contract=off.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -157,6 +158,75 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
             else if (!leaf_ref(c, ref)) { err = "BVH leaf range out of bounds"; return RT_ERR_INVALID; }
             put_child(q, w, c, ref);
         }
+    }
+
+    // ---- 4-wide collapse for the fast build: every other level of the reference tree is skipped ----
+    // A BVH4 node holds the (up to four) grandchildren of a reference inner node — a child that is a leaf stays
+    // as it is — in left-to-right order, boxes as SoA rows: minx[4] miny[4] minz[4] maxx[4] maxy[4] maxz[4]
+    // refs[4] pad[4] = 128 bytes.  Leaf references and triangle slots are shared with the 2-wide layout.
+    {
+        std::vector<int32_t> idx4(nb, -1);
+        std::vector<uint32_t> order4;
+        std::vector<uint32_t> stack4;
+        auto kids_of = [&](uint32_t n2, uint32_t* kids) -> int {
+            int c = 0;
+            for (int w = 0; w < 2; w++) {
+                const uint32_t ch = (uint32_t)d.bvh[n2].idx + (uint32_t)w;
+                if (is_inner(d.bvh[ch])) { kids[c++] = (uint32_t)d.bvh[ch].idx; kids[c++] = (uint32_t)d.bvh[ch].idx + 1; }
+                else kids[c++] = ch;
+            }
+            return c;
+        };
+        if (is_inner(d.bvh[0])) stack4.push_back(0);
+        while (!stack4.empty()) {
+            const uint32_t n2 = stack4.back();
+            stack4.pop_back();
+            idx4[n2] = (int32_t)order4.size();
+            order4.push_back(n2);
+            uint32_t kids[4];
+            const int c = kids_of(n2, kids);
+            for (int i = c - 1; i >= 0; i--)
+                if (is_inner(d.bvh[kids[i]])) stack4.push_back(kids[i]);
+        }
+        const size_t n4 = order4.empty() ? 1 : order4.size();
+        out.nodes4.assign(32 * n4, 0.0f);
+        for (size_t k = 0; k < n4; k++) { // all slots empty by default: box at +inf, ref NONE
+            float* q = &out.nodes4[32 * k];
+            for (int i = 0; i < 24; i++) q[i] = INFINITY;
+            const int32_t none = RT_REF_NONE_HOST;
+            for (int i = 0; i < 4; i++) std::memcpy(&q[24 + i], &none, 4);
+        }
+        auto put4 = [&](float* q, int slot, const rt_bvh_node& c, int32_t ref) {
+            if (ref == RT_REF_NONE_HOST) return;
+            q[0 + slot] = c.min[0]; q[4 + slot] = c.min[1]; q[8 + slot] = c.min[2];
+            q[12 + slot] = c.max[0]; q[16 + slot] = c.max[1]; q[20 + slot] = c.max[2];
+            std::memcpy(&q[24 + slot], &ref, 4);
+        };
+        if (order4.empty()) {
+            int32_t ref;
+            leaf_ref(d.bvh[0], ref);
+            rt_bvh_node all = d.bvh[0];
+            for (int a = 0; a < 3; a++) { all.min[a] = -1e30f; all.max[a] = 1e30f; }
+            put4(out.nodes4.data(), 0, all, ref);
+        }
+        // stack need of a ray: at a node with c live children one is entered and at most c-1 stay pushed
+        std::vector<int32_t> need4(n4, 0);
+        for (size_t k = order4.size(); k-- > 0;) { // children have larger indices than their parent (pre-order)
+            uint32_t kids[4];
+            const int c = kids_of(order4[k], kids);
+            float* q = &out.nodes4[32 * k];
+            int live = 0, deepest = 0;
+            for (int i = 0; i < c; i++) {
+                const rt_bvh_node& ch = d.bvh[kids[i]];
+                int32_t ref;
+                if (is_inner(ch)) { ref = idx4[kids[i]]; deepest = std::max(deepest, need4[(size_t)ref]); }
+                else if (!leaf_ref(ch, ref)) { err = "BVH leaf range out of bounds"; return RT_ERR_INVALID; }
+                if (ref != RT_REF_NONE_HOST) live++;
+                put4(q, i, ch, ref);
+            }
+            need4[k] = std::max(live - 1, 0) + deepest;
+        }
+        out.stack_need4 = (order4.empty() ? 0 : need4[0]) + 3; // + sentinel, postponed leaf, slack
     }
     return RT_OK;
 }

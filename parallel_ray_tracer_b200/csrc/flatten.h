@@ -15,6 +15,7 @@ namespace rt {
 
 struct FlatScene {
     std::vector<float>   nodes;    // 16 floats (4 x float4) per inner node
+    std::vector<float>   nodes4;   // 32 floats (8 x float4) per 4-wide node (fast build)
     std::vector<float>   tris;     // 16 floats (4 x float4) per leaf-order slot
     std::vector<float>   shade;    // 4 floats per original triangle
     std::vector<float>   mats;     // 12 floats per material
@@ -23,10 +24,11 @@ struct FlatScene {
     uint32_t n_lights = 0;
     float ambient[3] = {0, 0, 0};
     int max_depth = 0;
+    int stack_need4 = 0;           // stack slots a ray can need on the 4-wide tree
 
     size_t bytes() const
     {
-        return 4 * (nodes.size() + tris.size() + shade.size() + mats.size() + lights.size() + leaf_cnt.size());
+        return 4 * (nodes.size() + nodes4.size() + tris.size() + shade.size() + mats.size() + lights.size() + leaf_cnt.size());
     }
 };
 

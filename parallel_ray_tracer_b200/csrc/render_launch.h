@@ -8,6 +8,7 @@ struct RtLaunchCfg {
     int min_ctas;       // __launch_bounds__ second argument: caps registers/thread
     bool work_counters; // RT_AOV_WORK build (counts inner visits and triangle tests)
     bool speculative;   // fast build: speculative traversal (postponed leaves)
+    bool wide;          // fast build: 4-wide tree (implies speculative)
     int grid;           // number of persistent CTAs
 };
 

@@ -5,29 +5,25 @@ namespace RT_KERNEL_NS {
 
 typedef void (*kernel_fn)(const RtDeviceScene, const RtFrameArgs);
 
-template <bool WORK, bool SPEC>
+template <bool WORK, bool SPEC, bool WIDE>
 static kernel_fn pick(int block, int minb)
 {
-    if (block == 64) {
-        if (minb >= 16) return render_kernel<64, 16, WORK, SPEC>;
-        if (minb >= 12) return render_kernel<64, 12, WORK, SPEC>;
-        return render_kernel<64, 8, WORK, SPEC>;
-    }
-    if (minb >= 8) return render_kernel<128, 8, WORK, SPEC>;
-    if (minb >= 6) return render_kernel<128, 6, WORK, SPEC>;
-    if (minb >= 5) return render_kernel<128, 5, WORK, SPEC>;
-    if (minb >= 4) return render_kernel<128, 4, WORK, SPEC>;
-    return render_kernel<128, 3, WORK, SPEC>;
+    if (block == 64) return render_kernel<64, 12, WORK, SPEC, WIDE>;
+    if (minb >= 8) return render_kernel<128, 8, WORK, SPEC, WIDE>;
+    if (minb >= 6) return render_kernel<128, 6, WORK, SPEC, WIDE>;
+    if (minb >= 5) return render_kernel<128, 5, WORK, SPEC, WIDE>;
+    return render_kernel<128, 4, WORK, SPEC, WIDE>;
 }
 
 static kernel_fn pick(const RtLaunchCfg& c)
 {
 #if RT_STRICT
-    // the strict build never speculates: its visit order is the reference's, node for node
-    return c.work_counters ? pick<true, false>(c.block_threads, c.min_ctas) : pick<false, false>(c.block_threads, c.min_ctas);
+    // the strict build never speculates and never uses the 4-wide tree: its visit order is the reference's
+    return c.work_counters ? pick<true, false, false>(c.block_threads, c.min_ctas) : pick<false, false, false>(c.block_threads, c.min_ctas);
 #else
-    if (c.speculative) return c.work_counters ? pick<true, true>(c.block_threads, c.min_ctas) : pick<false, true>(c.block_threads, c.min_ctas);
-    return c.work_counters ? pick<true, false>(c.block_threads, c.min_ctas) : pick<false, false>(c.block_threads, c.min_ctas);
+    if (c.wide) return c.work_counters ? pick<true, true, true>(c.block_threads, c.min_ctas) : pick<false, true, true>(c.block_threads, c.min_ctas);
+    if (c.speculative) return c.work_counters ? pick<true, true, false>(c.block_threads, c.min_ctas) : pick<false, true, false>(c.block_threads, c.min_ctas);
+    return c.work_counters ? pick<true, false, false>(c.block_threads, c.min_ctas) : pick<false, false, false>(c.block_threads, c.min_ctas);
 #endif
 }
 

@@ -27,7 +27,7 @@ struct Dev {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     // scene (replicated per device)
-    float4 *nodes = nullptr, *tris = nullptr, *shade = nullptr, *mats = nullptr, *lights = nullptr;
+    float4 *nodes = nullptr, *nodes4 = nullptr, *tris = nullptr, *shade = nullptr, *mats = nullptr, *lights = nullptr;
     int* leaf_cnt = nullptr;
     // per-frame control block: [0..3] stats (u64), then the tile counter
     unsigned long long* ctrl = nullptr;
@@ -74,7 +74,7 @@ struct rt_ctx {
     uchar4* ipc_frame = nullptr;
     int ipc_w = 0, ipc_h = 0;
     size_t scene_bytes = 0;
-    int max_depth = 0;
+    int max_depth = 0, stack_need4 = 0;
     bool want_trace = false;
 };
 
@@ -211,7 +211,7 @@ int setup_local_index(rt_ctx* c, int w, int h, int parts)
 void free_dev(Dev& D)
 {
     cudaSetDevice(D.id);
-    cudaFree(D.nodes); cudaFree(D.tris); cudaFree(D.shade); cudaFree(D.mats); cudaFree(D.lights);
+    cudaFree(D.nodes); cudaFree(D.nodes4); cudaFree(D.tris); cudaFree(D.shade); cudaFree(D.mats); cudaFree(D.lights);
     cudaFree(D.leaf_cnt); cudaFree(D.ctrl); cudaFree(D.tile_list); cudaFree(D.warp_trace);
     cudaFree(D.bgra); cudaFree(D.packed); cudaFree(D.rgb); cudaFree(D.tri_id); cudaFree(D.depth);
     if (D.ctrl_host) cudaFreeHost(D.ctrl_host);
@@ -281,6 +281,7 @@ int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** 
     rt_ctx* c = new rt_ctx();
     c->scene_bytes = flat.bytes();
     c->max_depth = flat.max_depth;
+    c->stack_need4 = flat.stack_need4;
     c->scene_host_view.n_lights = (int)flat.n_lights;
     std::memcpy(c->scene_host_view.amb, flat.ambient, 12);
     c->devs.resize(ndev);
@@ -296,6 +297,7 @@ int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** 
         CKC(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
         CKC(cudaEventCreate(&D.ev0)); CKC(cudaEventCreate(&D.ev1)); CKC(cudaEventCreate(&D.ev2));
         CKC(upload(&D.nodes, flat.nodes.data(), flat.nodes.size() * 4, D.stream));
+        CKC(upload(&D.nodes4, flat.nodes4.data(), flat.nodes4.size() * 4, D.stream));
         CKC(upload(&D.tris, flat.tris.data(), flat.tris.size() * 4, D.stream));
         CKC(upload(&D.shade, flat.shade.data(), flat.shade.size() * 4, D.stream));
         CKC(upload(&D.mats, flat.mats.data(), flat.mats.size() * 4, D.stream));
@@ -384,6 +386,8 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
     cfg.min_ctas = p->ctas_per_sm > 0 ? p->ctas_per_sm : (cfg.block_threads == 64 ? 12 : 6); // 24 warps/SM: profiles/r01_notes.md
     cfg.work_counters = (p->aov_mask & RT_AOV_WORK) != 0;
     cfg.speculative = p->traversal != RT_TRAVERSAL_PLAIN;
+    // the 4-wide tree is the default of the fast build whenever its worst-case stack need fits
+    cfg.wide = (p->traversal == RT_TRAVERSAL_DEFAULT || p->traversal == RT_TRAVERSAL_WIDE) && c->stack_need4 <= RT_STACK_ENTRIES_WIDE;
     fa.refill_threshold = p->refill_threshold > 0 ? std::min(p->refill_threshold, 32) : 20;
 
     unsigned launches = 0;
@@ -408,7 +412,7 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
         Dev& D = c->devs[d];
         CK(c, cudaSetDevice(D.id));
         RtDeviceScene sc = c->scene_host_view;
-        sc.nodes = D.nodes; sc.tris = D.tris; sc.shade = D.shade;
+        sc.nodes = D.nodes; sc.nodes4 = D.nodes4; sc.tris = D.tris; sc.shade = D.shade;
         sc.mats = D.mats; sc.lights = D.lights; sc.leaf_cnt = D.leaf_cnt;
         RtFrameArgs f = fa;
         f.tile_list = D.tile_list; f.n_tiles = D.n_tiles;

@@ -65,6 +65,21 @@ def test_fast_vs_oracle(rt, gpu_scenes, oracle_scenes, manifest, scene, cam):
 
 
 @pytest.mark.parametrize("scene", SCENES)
+@pytest.mark.parametrize("traversal", [1, 2, 3])
+def test_fast_traversal_variants_give_the_same_image(rt, gpu_scenes, oracle_scenes, scene, traversal):
+    """RT_TRAVERSAL_PLAIN / SPECULATIVE / WIDE only change the visit order: depth and colour must agree with
+    the oracle to the fast-build tolerances, and any two variants with each other on every non-tie pixel."""
+    w, h = 480, 270
+    ref = oracle_scenes[scene].render(w, h)
+    got = render(rt, gpu_scenes[scene][1], w, h, rt.RT_MODE_FAST, traversal=traversal)
+    assert_fast_parity(O.compare_aovs(got, ref))
+    base = render(rt, gpu_scenes[scene][1], w, h, rt.RT_MODE_FAST, traversal=1)
+    same = (got["id"] == base["id"])
+    assert same.mean() >= 0.9999
+    assert np.array_equal(got["depth"][same], base["depth"][same])   # identical arithmetic on identical hits
+
+
+@pytest.mark.parametrize("scene", SCENES)
 @pytest.mark.parametrize("cam", ["default", "yaw"])
 @pytest.mark.parametrize("mode", ["fast", "strict"])
 def test_vs_reference_golden_aovs(rt, gpu_scenes, manifest, scene, cam, mode):
