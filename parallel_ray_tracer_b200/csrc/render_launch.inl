@@ -10,6 +10,7 @@ static kernel_fn pick(int block, int minb)
 {
     if (block == 64) return render_kernel<64, 12, WORK, SPEC, WIDE>;
     if (minb >= 8) return render_kernel<128, 8, WORK, SPEC, WIDE>;
+    if (minb >= 7) return render_kernel<128, 7, WORK, SPEC, WIDE>;
     if (minb >= 6) return render_kernel<128, 6, WORK, SPEC, WIDE>;
     if (minb >= 5) return render_kernel<128, 5, WORK, SPEC, WIDE>;
     return render_kernel<128, 4, WORK, SPEC, WIDE>;

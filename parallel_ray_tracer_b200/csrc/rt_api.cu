@@ -383,11 +383,16 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
 
     RtLaunchCfg cfg;
     cfg.block_threads = p->block_threads == 64 ? 64 : 128;
-    cfg.min_ctas = p->ctas_per_sm > 0 ? p->ctas_per_sm : (cfg.block_threads == 64 ? 12 : 6); // 24 warps/SM: profiles/r01_notes.md
+    // Defaults (profiles/r01_notes.md): small frames are bounded by the dependent chain of their longest pixels, which the
+    // 4-wide tree halves; large frames are throughput-bound, where the 2-wide tree with 28 warps/SM (72 registers) wins.
+    const double px_per_part = (double)w * h * p->spp / (double)(part_count * (int)c->devs.size());
+    const bool small_frame = px_per_part <= 4.0e6;
+    const bool want_wide = p->traversal == RT_TRAVERSAL_WIDE || (p->traversal == RT_TRAVERSAL_DEFAULT && small_frame);
+    cfg.min_ctas = p->ctas_per_sm > 0 ? p->ctas_per_sm : (cfg.block_threads == 64 ? 12 : (want_wide ? 6 : 7));
     cfg.work_counters = (p->aov_mask & RT_AOV_WORK) != 0;
     cfg.speculative = p->traversal != RT_TRAVERSAL_PLAIN;
-    // the 4-wide tree is the default of the fast build whenever its worst-case stack need fits
-    cfg.wide = (p->traversal == RT_TRAVERSAL_DEFAULT || p->traversal == RT_TRAVERSAL_WIDE) && c->stack_need4 <= RT_STACK_ENTRIES_WIDE;
+    // (the 4-wide tree is only used when its worst-case stack need fits the shared stack)
+    cfg.wide = want_wide && c->stack_need4 <= RT_STACK_ENTRIES_WIDE;
     fa.refill_threshold = p->refill_threshold > 0 ? std::min(p->refill_threshold, 32) : 20;
 
     unsigned launches = 0;
