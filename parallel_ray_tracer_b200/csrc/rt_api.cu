@@ -422,7 +422,7 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
         RtFrameArgs f = fa;
         f.tile_list = D.tile_list; f.n_tiles = D.n_tiles;
         f.stats = D.ctrl; f.tile_counter = reinterpret_cast<unsigned*>(D.ctrl + 4);
-        f.sm_cursor = D.ctrl + 8;
+        f.sm_cursor = small_frame ? nullptr : D.ctrl + 8; // SM-local work queues pay off on throughput-bound frames only
         f.n_sms = (unsigned)std::min(D.sm_count, RT_MAX_SMS);
         const bool local = (d > 0 && gather == RT_GATHER_PEER_COPY);
         f.bgra = local ? D.bgra : (c->ipc_frame ? c->ipc_frame : D0.bgra); // peer-mapped for d > 0
