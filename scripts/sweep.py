@@ -29,7 +29,7 @@ def main():
         sc = rt.Scene.load_rtsc(ROOT / "tests" / "golden" / "scenes" / f"{scene}.rtsc").build_bvh(6)
         ctx = rt.Context(sc, [0])
         for mode in (rt.RT_MODE_STRICT, rt.RT_MODE_FAST):
-            grid = [(b, c, r, 2, f) for rep in (0, 1) for f in (0,) for (b, c) in ((128, 6), (128, 4), (64, 12)) for r in (16, 20)]
+            grid = [(b, c, r, t, 0) for rep in (0, 1) for (b, c) in ((128, 6), (128, 7), (64, 12)) for t in (2, 3) for r in (12, 16, 20, 24, 28)]
             if mode == rt.RT_MODE_STRICT:
                 grid = [(128, 5, 24, 1, 2), (128, 5, 24, 1, 2)]
             for block, ctas, refill, trav, fb in grid:
