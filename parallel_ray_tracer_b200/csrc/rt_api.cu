@@ -75,6 +75,9 @@ struct rt_ctx {
     int ipc_w = 0, ipc_h = 0;
     size_t scene_bytes = 0;
     int max_depth = 0, stack_need4 = 0;
+    // rays per device of the last frame and the shape they belong to (scheduling default, see rt_render)
+    double rays_per_dev = 0;
+    int rays_w = 0, rays_h = 0, rays_spp = 0, rays_parts = 0;
     bool want_trace = false;
 };
 
@@ -385,8 +388,11 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
     cfg.block_threads = p->block_threads == 64 ? 64 : 128;
     // Defaults (profiles/r01_notes.md): small frames are bounded by the dependent chain of their longest pixels, which the
     // 4-wide tree halves; large frames are throughput-bound, where the 2-wide tree with 28 warps/SM (72 registers) wins.
+    // "Small" is decided by the rays the previous frame of the same shape actually traced on this context (8 M per GPU),
+    // and by the pixel-sample count (4 M per GPU) for a first frame.
     const double px_per_part = (double)w * h * p->spp / (double)(part_count * (int)c->devs.size());
-    const bool small_frame = px_per_part <= 4.0e6;
+    const bool same_shape = c->rays_w == w && c->rays_h == h && c->rays_spp == p->spp && c->rays_parts == part_count;
+    const bool small_frame = same_shape ? c->rays_per_dev <= 8.0e6 : px_per_part <= 4.0e6;
     const bool want_wide = p->traversal == RT_TRAVERSAL_WIDE || (p->traversal == RT_TRAVERSAL_DEFAULT && small_frame);
     cfg.min_ctas = p->ctas_per_sm > 0 ? p->ctas_per_sm : (cfg.block_threads == 64 ? 12 : (want_wide ? 6 : 7));
     cfg.work_counters = (p->aov_mask & RT_AOV_WORK) != 0;
@@ -529,6 +535,8 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
         t.inner_visits += D.ctrl_host[2];
         t.tri_tests += D.ctrl_host[3];
     }
+    c->rays_per_dev = (double)(t.rays_closest + t.rays_shadow) / nd;
+    c->rays_w = w; c->rays_h = h; c->rays_spp = p->spp; c->rays_parts = part_count;
     t.gather_ms = gather_ms;
     t.total_ms = kmax + gather_ms;
     t.launches = launches;
