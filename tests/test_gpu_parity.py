@@ -73,10 +73,12 @@ def test_fast_traversal_variants_give_the_same_image(rt, gpu_scenes, oracle_scen
     ref = oracle_scenes[scene].render(w, h)
     got = render(rt, gpu_scenes[scene][1], w, h, rt.RT_MODE_FAST, traversal=traversal)
     assert_fast_parity(O.compare_aovs(got, ref))
+    # Only exactly equal t from two triangles could make the visit order visible; the shipped scenes have no such
+    # ties, so every variant gives the same bits (this is what lets the library switch variants between frames).
     base = render(rt, gpu_scenes[scene][1], w, h, rt.RT_MODE_FAST, traversal=1)
-    same = (got["id"] == base["id"])
-    assert same.mean() >= 0.9999
-    assert np.array_equal(got["depth"][same], base["depth"][same])   # identical arithmetic on identical hits
+    assert np.array_equal(got["id"], base["id"])
+    assert np.array_equal(got["depth"].view(np.uint32), base["depth"].view(np.uint32))
+    assert np.array_equal(got["rgb"].view(np.uint32), base["rgb"].view(np.uint32))
 
 
 @pytest.mark.parametrize("scene", SCENES)
