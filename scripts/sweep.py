@@ -34,7 +34,6 @@ def main():
                 grid = [(128, 5, 24, 1, 2), (128, 5, 24, 1, 2)]
             for block, ctas, refill, trav, fb in grid:
                 p = rt.default_params(width=w, height=h, mode=mode, block_threads=block, ctas_per_sm=ctas, refill_threshold=refill, traversal=trav)
-                p.reserved[0] = fb
                 ms = []
                 import time
                 t_end = time.perf_counter() + 0.15   # >= 150 ms of warm-up per configuration (clock ramp)
