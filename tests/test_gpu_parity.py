@@ -247,6 +247,25 @@ def test_partitioned_render_assembles_to_the_single_frame(rt, gpu_scenes, parts)
     assert np.array_equal(ctx.load_from_gpu()["bgra"], full)
 
 
+def test_cpp_host_driver_writes_the_reference_bmp(rt, oracle_scenes, tmp_path):
+    """csrc/rt_render_main.cpp (the reference main() re-stated above the C-ABI): load, build, render, write BMP.  The
+    file must be the BMP of the oracle's frame: 54-byte header, bottom-up BGRA rows (cpu/src/bmp_writer.c)."""
+    import subprocess
+    exe = rt.PKG_DIR / "rt_render"
+    if not exe.exists():
+        pytest.skip("rt_render not built")
+    out = tmp_path / "o.bmp"
+    r = subprocess.run([str(exe), "--rtsc", str(O.HERE.parent / "tests" / "golden" / "scenes" / "car_only.rtsc"), "--width", "320", "--height", "180",
+                        "--strict", "--iterations", "3", "--warmup", "1", "--out", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Frame time (median)" in r.stdout and "Mrays/s" in r.stdout
+    raw = out.read_bytes()
+    assert len(raw) == 54 + 4 * 320 * 180 and raw[:2] == b"BM"
+    rows = np.frombuffer(raw, np.uint8, 4 * 320 * 180, 54).reshape(180, 320, 4)[::-1]
+    ref = oracle_scenes["car_only"].render(320, 180)
+    assert np.array_equal(rows, ref["bgra"])
+
+
 def test_error_paths(rt, gpu_scenes):
     sc, ctx = gpu_scenes["soup2k"]
     with pytest.raises(rt.RtError):
