@@ -17,7 +17,8 @@ NCCL all-gather, unpack kernel).  Total work is fixed as N grows: "scaling": "st
          max over ranks); L2 is flushed between timed frames (a 512 MiB buffer is overwritten)
   e2e    same metric by wall clock through the public API with HOST buffers: per step the camera /
          render parameters go host->device (kernel arguments), the frame is assembled and the 8-bit
-         frame is copied device->host into pinned memory (rt_download)
+         frame is copied device->host into pinned memory; frames are queued as a sequence, so frame
+         k+1 renders while frame k is copied (rt_render_async / rt_download_async / rt_frame_wait)
   rays   one ray = one closest-hit or one shadow traversal; counted by the kernel and
          checked against the oracle's count in tests/test_gpu_parity.py
 
@@ -205,12 +206,13 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
     gather = args.gather if world > 1 else "none"
     if gather == "ipc":
         try:
-            h = torch.zeros(64, dtype=torch.uint8, device=dev)
-            if rank == 0:
-                h.copy_(torch.frombuffer(bytearray(ctx.frame_ipc_export(W, H)), dtype=torch.uint8))
-            dist.broadcast(h, 0)
-            if rank != 0:
-                ctx.frame_ipc_import(bytes(h.cpu().numpy().tobytes()), W, H)
+            for slot in range(rt.RT_FRAME_SLOTS):   # both frame slots of rank 0 become peer-store targets
+                h = torch.zeros(64, dtype=torch.uint8, device=dev)
+                if rank == 0:
+                    h.copy_(torch.frombuffer(bytearray(ctx.frame_ipc_export(W, H, slot)), dtype=torch.uint8))
+                dist.broadcast(h, 0)
+                if rank != 0:
+                    ctx.frame_ipc_import(bytes(h.cpu().numpy().tobytes()), W, H, slot)
             ok = torch.ones(1, device=dev)
         except rt.RtError as e:
             print(f"[rank {rank}] CUDA IPC mapping failed ({e}); falling back to --gather nccl", file=sys.stderr)
@@ -225,7 +227,7 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
         recv = torch.zeros(stride * world, dtype=torch.uint8, device=dev)
 
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    pinned = torch.empty(W * H * 4, dtype=torch.uint8).pin_memory()
+    pinned = [torch.empty(W * H * 4, dtype=torch.uint8).pin_memory() for _ in range(rt.RT_FRAME_SLOTS)]
 
     def assemble() -> float:
         """Unfused path: packed tiles -> NCCL all-gather -> unpack on rank 0.  Returns device ms."""
@@ -276,17 +278,58 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
         tm2, ms = step(False)
         warm.append(ms)
 
-    # ---- e2e: public API, host buffers, D2H of the frame inside the timed region ----
+    # ---- e2e: public API, host buffers, every frame's D2H inside the timed region ----
+    # Frame sequence as the reference runs it (ITERATIONS frames, gpu/src/main.cu:111-114), through the sequence API:
+    # frame k renders into frame slot k % 2 while frame k-1 is copied device->host on a second stream
+    # (rt_render_async / rt_download_async / rt_frame_wait).  Per step: render parameters H2D (kernel arguments),
+    # the assembled 8-bit frame D2H into pinned memory.  With the unfused NCCL gather the steps stay synchronous.
+    slot_params = []
+    for slot in range(rt.RT_FRAME_SLOTS):
+        slot_params.append(rt.default_params(**base, frame_slot=slot))
     barrier(); torch.cuda.synchronize()
     t_e0 = time.perf_counter()
+    if gather == "nccl":
+        for _ in range(args.steps):
+            ctx.render_frame(params)
+            assemble()
+            barrier()
+            if rank == 0:
+                ctx.download_into(pinned[0].data_ptr())
+    elif world == 1:
+        for k in range(args.steps):
+            s = k % rt.RT_FRAME_SLOTS
+            if k >= rt.RT_FRAME_SLOTS:
+                ctx.frame_wait(s)           # frame k-2 is on the host (pinned[s] is consumed here)
+            ctx.render_frame_async(slot_params[s])
+            ctx.download_async(s, pinned[s].data_ptr())
+        for s in range(min(args.steps, rt.RT_FRAME_SLOTS)):
+            ctx.frame_wait(s)
+    else:
+        for k in range(args.steps):
+            s = k % rt.RT_FRAME_SLOTS
+            ctx.render_frame_async(slot_params[s])
+            ctx.frame_wait(s)               # this rank's tiles of frame k are stored in rank 0's slot s
+            if rank == 0 and k >= 1:
+                ctx.frame_wait(1 - s)       # D2H of frame k-1 (ran during this render) is complete: slot 1-s is free again
+            barrier()                       # frame k on rank 0 is complete once every rank has stored its tiles
+            if rank == 0:
+                ctx.download_async(s, pinned[s].data_ptr())
+        if rank == 0:
+            for s in range(min(args.steps, rt.RT_FRAME_SLOTS)):
+                ctx.frame_wait(s)
+    torch.cuda.synchronize(); barrier()
+    e2e_ms = (time.perf_counter() - t_e0) * 1e3 / args.steps
+    # unpipelined reference point: render, wait, copy, wait — one frame at a time
+    barrier(); torch.cuda.synchronize()
+    t_s0 = time.perf_counter()
     for _ in range(args.steps):
         ctx.render_frame(params)
         assemble()
-        barrier()                       # the frame on rank 0 is complete once every rank has stored its tiles
+        barrier()
         if rank == 0:
-            ctx.download_into(pinned.data_ptr())
+            ctx.download_into(pinned[0].data_ptr())
     torch.cuda.synchronize(); barrier()
-    e2e_ms = (time.perf_counter() - t_e0) * 1e3 / args.steps
+    e2e_sync_ms = (time.perf_counter() - t_s0) * 1e3 / args.steps
 
     # ---- reductions over ranks ----
     def allmax(x):
@@ -302,6 +345,7 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
     total_warm_ms = allmax(sum(warm))
     wall_ms = allmax(wall_ms)
     e2e_ms = allmax(e2e_ms)
+    e2e_sync_ms = allmax(e2e_sync_ms)
     rays = int(allsum(rays_local))
     launches = int(allsum(launches))
 
@@ -377,7 +421,10 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
                           "scene_note": "car_only as shipped by the reference; substitutions for missing scenes in DESIGN.md"},
                "clocks": clocks,
                "e2e": {"value": rays / e2e_ms / 1e3, "unit": METRIC, "ms_per_step": e2e_ms,
-                       "h2d_bytes_per_step": C.sizeof(rt.rt_render_params) * world, "d2h_bytes_per_step": W * H * 4},
+                       "h2d_bytes_per_step": C.sizeof(rt.rt_render_params) * world, "d2h_bytes_per_step": W * H * 4,
+                       "pipeline": ("synchronous (NCCL gather)" if gather == "nccl" else
+                                    "frame k+1 renders while frame k is copied device->host (2 frame slots, rt_render_async / rt_download_async)"),
+                       "value_unpipelined": rays / e2e_sync_ms / 1e3, "ms_per_step_unpipelined": e2e_sync_ms},
                "gpu_launches": launches,
                "rays_per_frame": rays, "primary_mrays_s": W * H * SPP / ms_per_step / 1e3,
                "value_l2_warm": rays / (total_warm_ms / args.steps) / 1e3,

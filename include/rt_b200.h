@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2
 #define RT_MAX_DEVICES 16
 
 typedef enum rt_status {
@@ -147,6 +147,15 @@ enum { /* rt_render_params.gather */
     RT_GATHER_PEER_COPY = 1   /* unfused: local frame, then packed tile copy device->device 0 + unpack */
 };
 
+/* Frame sequences (the reference's ITERATIONS loop, cpu/src/main.c:169-185, gpu/src/main.cu:111-114): a context
+ * owns RT_FRAME_SLOTS device frames, so that frame k+1 can render while frame k is copied to the host. */
+#define RT_FRAME_SLOTS 2
+enum { /* rt_render_params.frame_flags */
+    RT_FRAME_BOTTOM_UP = 1 /* store the BGRA rows bottom-up — the BMP row order (cpu/src/bmp_writer.c:122-146) — so that
+                              the downloaded buffer IS the BMP pixel array and no host-side row flip is left.  AOVs stay
+                              top-down.  Not available with RT_GATHER_PEER_COPY / packed tiles. */
+};
+
 typedef struct rt_render_params {
     rt_camera cam;
     int32_t   width, height;
@@ -165,7 +174,9 @@ typedef struct rt_render_params {
     int32_t   ctas_per_sm;      /* persistent CTAs per SM */
     int32_t   refill_threshold; /* leave the traversal loop when fewer lanes than this are active */
     int32_t   traversal;        /* RT_TRAVERSAL_* (fast mode only; strict always walks the reference order) */
-    int32_t   reserved[4];
+    int32_t   frame_flags;      /* RT_FRAME_* */
+    int32_t   frame_slot;       /* which of the context's RT_FRAME_SLOTS device frames to render into (frame sequences) */
+    int32_t   reserved[2];
 } rt_render_params;
 
 typedef struct rt_timing {
@@ -187,13 +198,28 @@ void rt_render_params_default(rt_render_params* p); /* reference defaults: 1920x
 int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** out);
 /* render_frame: blocking; renders into device-resident frame(s). */
 int rt_render(rt_ctx* ctx, const rt_render_params* params, rt_timing* timing_out);
-/* load_from_gpu: copy the last frame to host.  bgra: W*H*4 bytes, row 0 = top, bytes
+/* load_from_gpu: copy the last rendered frame (of the slot rendered last) to host; blocking.  bgra: W*H*4 bytes, row 0 = top, bytes
  * B,G,R,255 exactly as vec_to_bgra (cpu/src/bmp_writer.c:88-95).  The other outputs are
  * optional (NULL) and require the matching RT_AOV_* bit in the last rt_render. */
 int rt_download(rt_ctx* ctx, uint8_t* bgra, float* rgb, int32_t* tri_id, float* depth_t);
 void rt_destroy(rt_ctx* ctx);
 /* Message of the last failure on this context (ctx == NULL: of the calling thread). */
 const char* rt_last_error(const rt_ctx* ctx);
+
+/* -------- frame sequences: non-blocking render + overlapped device->host copy --------
+ * rt_render_async queues a frame on params->frame_slot and returns without waiting for the device (with
+ * RT_GATHER_PEER_COPY the gather still blocks).  rt_download_async queues the copy of that slot's BGRA frame to
+ * `host_bgra` (W*H*4 bytes; pinned memory — rt_host_alloc — makes it a true asynchronous copy) on a second
+ * stream, ordered after the slot's render on every device of the context.  rt_frame_wait blocks until everything
+ * queued on the slot so far (render, then copy) is complete and returns the render's timing.  A slot must be
+ * waited on before it is rendered into again; a copy still pending on it is ordered before the new render.
+ *     rt_render(ctx, p, tm)  ==  rt_render_async(ctx, p); rt_frame_wait(ctx, p->frame_slot, tm)            */
+int rt_render_async(rt_ctx* ctx, const rt_render_params* params);
+int rt_download_async(rt_ctx* ctx, int slot, uint8_t* host_bgra);
+int rt_frame_wait(rt_ctx* ctx, int slot, rt_timing* timing_out);
+/* Page-locked host memory for rt_download / rt_download_async targets (cudaHostAlloc / cudaFreeHost). */
+int rt_host_alloc(size_t bytes, void** out);
+void rt_host_free(void* p);
 
 /* -------- one-process-per-GPU frame assembly (torch.distributed / NCCL plumbing) -------- */
 /* Tile geometry shared by the kernel, the pack/unpack kernels and the host. */
@@ -218,14 +244,21 @@ int rt_unpack_tiles(rt_ctx* ctx, const void* dev_gathered, size_t stride_bytes, 
  * process's frame the peer-store target of this context's renders. */
 int rt_frame_ipc_export(rt_ctx* ctx, int width, int height, void* handle64);
 int rt_frame_ipc_import(rt_ctx* ctx, const void* handle64, int width, int height);
+/* Same for frame slot `slot` (the two calls above are slot 0). */
+int rt_frame_ipc_export_slot(rt_ctx* ctx, int slot, int width, int height, void* handle64);
+int rt_frame_ipc_import_slot(rt_ctx* ctx, int slot, const void* handle64, int width, int height);
 /* Diagnostics: per-warp timeline of RT_AOV_WORK renders (8 x u64 per warp, see csrc/rt_api.cu). */
 int rt_debug_warp_trace(rt_ctx* ctx, int enable, unsigned long long* out, int max_warps);
+/* Diagnostics: replace the first device's tile order (tile ids, ty * tiles_x + tx) for the current frame shape. */
+int rt_debug_set_tile_order(rt_ctx* ctx, const unsigned* tiles, int n);
 /* Raw device pointer of the BGRA frame (device 0 of the context). */
 int rt_frame_device_ptr(rt_ctx* ctx, void** dev_ptr, size_t* bytes);
 
 /* -------- image output (cpu/src/bmp_writer.c:177-211) -------- */
 /* 54-byte header, 32 bpp, bottom-up rows; input is the top-down BGRA of rt_download. */
 int rt_write_bmp(const char* path, const uint8_t* bgra_top_down, int width, int height);
+/* Same file from a frame whose rows are already bottom-up (RT_FRAME_BOTTOM_UP): header + one write, no flip. */
+int rt_write_bmp_bottom_up(const char* path, const uint8_t* bgra_bottom_up, int width, int height);
 
 int rt_abi_version(void);
 /* number of visible CUDA devices (0 when there is none / no driver) */

@@ -34,6 +34,8 @@ RT_BVH_REFBIN = 0x100
 RT_TRAVERSAL_DEFAULT, RT_TRAVERSAL_PLAIN, RT_TRAVERSAL_SPECULATIVE, RT_TRAVERSAL_WIDE = 0, 1, 2, 3
 RT_TILE_W, RT_TILE_H = 16, 8
 RT_MAX_DEVICES = 16
+RT_FRAME_SLOTS = 2
+RT_FRAME_BOTTOM_UP = 1
 
 # every symbol include/rt_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -42,6 +44,8 @@ EXPORTS = [
     "rt_render_params_default", "rt_create", "rt_render", "rt_download", "rt_destroy", "rt_last_error",
     "rt_part_tile_count", "rt_packed_tiles", "rt_unpack_tiles", "rt_frame_ipc_export", "rt_frame_ipc_import",
     "rt_frame_device_ptr", "rt_write_bmp", "rt_abi_version", "rt_device_count", "rt_debug_warp_trace",
+    "rt_render_async", "rt_download_async", "rt_frame_wait", "rt_host_alloc", "rt_host_free",
+    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order",
 ]
 
 
@@ -70,7 +74,8 @@ class rt_render_params(C.Structure):
                 ("seed", C.c_uint32), ("bounces", C.c_int32), ("mode", C.c_int32), ("aov_mask", C.c_int32),
                 ("gather", C.c_int32), ("part_index", C.c_int32), ("part_count", C.c_int32),
                 ("block_threads", C.c_int32), ("ctas_per_sm", C.c_int32), ("refill_threshold", C.c_int32),
-                ("traversal", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("traversal", C.c_int32), ("frame_flags", C.c_int32), ("frame_slot", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
 
 
 class rt_timing(C.Structure):
@@ -126,6 +131,15 @@ def lib() -> C.CDLL:
     L.rt_frame_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.rt_write_bmp.argtypes = [C.c_char_p, vp, i32, i32]
     L.rt_debug_warp_trace.argtypes = [vp, i32, vp, i32]
+    L.rt_debug_set_tile_order.argtypes = [vp, vp, i32]
+    L.rt_render_async.argtypes = [vp, C.POINTER(rt_render_params)]
+    L.rt_download_async.argtypes = [vp, i32, vp]
+    L.rt_frame_wait.argtypes = [vp, i32, C.POINTER(rt_timing)]
+    L.rt_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.rt_host_free.argtypes = [vp]; L.rt_host_free.restype = None
+    L.rt_frame_ipc_export_slot.argtypes = [vp, i32, i32, i32, vp]
+    L.rt_frame_ipc_import_slot.argtypes = [vp, i32, vp, i32, i32]
+    L.rt_write_bmp_bottom_up.argtypes = [C.c_char_p, vp, i32, i32]
     _lib = L
     return L
 
@@ -282,6 +296,23 @@ class Context:
         self.last = (p.width, p.height, p.aov_mask)
         return t
 
+    # -- frame sequences (the reference's ITERATIONS loop): queue, copy on a second stream, wait
+    def render_frame_async(self, params: rt_render_params = None, **kw) -> int:
+        """rt_render_async: queue a frame on params.frame_slot; returns the slot."""
+        p = params if params is not None else default_params(**kw)
+        _check(lib().rt_render_async(self._h, C.byref(p)), self._h)
+        self.last = (p.width, p.height, p.aov_mask)
+        return p.frame_slot
+
+    def download_async(self, slot: int, host_ptr: int):
+        """rt_download_async: queue the copy of the slot's BGRA frame into (pinned) host memory."""
+        _check(lib().rt_download_async(self._h, slot, C.c_void_p(host_ptr)), self._h)
+
+    def frame_wait(self, slot: int) -> rt_timing:
+        t = rt_timing()
+        _check(lib().rt_frame_wait(self._h, slot, C.byref(t)), self._h)
+        return t
+
     def load_from_gpu(self, rgb=False, tri_id=False, depth=False, out_bgra=None) -> dict:
         """load_from_gpu (gpu/src/gpu.cu:203-228): frame (and optional AOVs) to host arrays."""
         w, h, _ = self.last
@@ -313,20 +344,24 @@ class Context:
         _check(lib().rt_frame_device_ptr(self._h, C.byref(p), C.byref(n)), self._h)
         return p.value, n.value
 
-    def frame_ipc_export(self, width, height) -> bytes:
+    def frame_ipc_export(self, width, height, slot=0) -> bytes:
         buf = C.create_string_buffer(64)
-        _check(lib().rt_frame_ipc_export(self._h, width, height, buf), self._h)
+        _check(lib().rt_frame_ipc_export_slot(self._h, slot, width, height, buf), self._h)
         return buf.raw
 
-    def frame_ipc_import(self, handle: bytes, width, height):
+    def frame_ipc_import(self, handle: bytes, width, height, slot=0):
         buf = C.create_string_buffer(handle, 64)
-        _check(lib().rt_frame_ipc_import(self._h, buf, width, height), self._h)
+        _check(lib().rt_frame_ipc_import_slot(self._h, slot, buf, width, height), self._h)
 
     def warp_trace(self, enable=True, max_warps=8192):
         """Diagnostics: arm / read the per-warp timeline of RT_AOV_WORK renders (see rt_debug_warp_trace)."""
         buf = np.zeros((max_warps, 8), np.uint64)
         n = lib().rt_debug_warp_trace(self._h, int(enable), _ptr(buf), max_warps)
         return buf[:max(n, 0)]
+
+    def set_tile_order(self, tiles):
+        t = np.ascontiguousarray(tiles, np.uint32)
+        _check(lib().rt_debug_set_tile_order(self._h, _ptr(t), len(t)), self._h)
 
     def close(self):
         if self._h:
@@ -345,6 +380,35 @@ def write_bmp(path, bgra: np.ndarray):
     bgra = np.ascontiguousarray(bgra, np.uint8)
     h, w = bgra.shape[:2]
     _check(lib().rt_write_bmp(str(path).encode(), _ptr(bgra), w, h))
+
+
+def write_bmp_bottom_up(path, bgra: np.ndarray):
+    """Same file from a frame rendered with RT_FRAME_BOTTOM_UP (rows already in BMP order): no flip."""
+    bgra = np.ascontiguousarray(bgra, np.uint8)
+    h, w = bgra.shape[:2]
+    _check(lib().rt_write_bmp_bottom_up(str(path).encode(), _ptr(bgra), w, h))
+
+
+class PinnedBuffer:
+    """Page-locked host memory from rt_host_alloc, viewed as a numpy uint8 array."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        _check(lib().rt_host_alloc(nbytes, C.byref(p)))
+        self.ptr = p.value
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), (nbytes,))
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            lib().rt_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def part_tile_count(width, height, part_index, part_count) -> int:

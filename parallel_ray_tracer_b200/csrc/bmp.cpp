@@ -8,13 +8,13 @@
 
 #include "host_scene.h"
 
-extern "C" int rt_write_bmp(const char* path, const uint8_t* bgra, int width, int height)
+static int write_bmp_rows(const char* path, const uint8_t* bgra, int width, int height, bool rows_bottom_up)
 {
     if (!path || !bgra || width <= 0 || height <= 0) { rt::set_error("rt_write_bmp: bad parameters"); return RT_ERR_INVALID; }
     const int row = width * 4, header = 14 + 40;
     const int file_size = header + row * height;
-    std::vector<uint8_t> buf((size_t)file_size, 0);
-    uint8_t* b = buf.data();
+    uint8_t b[14 + 40];
+    std::memset(b, 0, sizeof b);
     b[0] = 'B'; b[1] = 'M';
     std::memcpy(b + 0x02, &file_size, 4);
     std::memcpy(b + 0x0A, &header, 4);
@@ -25,12 +25,27 @@ extern "C" int rt_write_bmp(const char* path, const uint8_t* bgra, int width, in
     std::memcpy(b + 0x16, &height, 4);
     std::memcpy(b + 0x1A, &planes, 2);
     std::memcpy(b + 0x1C, &bpp, 2);
-    for (int y = 0; y < height; y++) // bottom-up
-        std::memcpy(b + header + (size_t)y * row, bgra + (size_t)(height - 1 - y) * row, (size_t)row);
     FILE* f = std::fopen(path, "wb");
     if (!f) { rt::set_error(std::string("Unable to open the BMP file ") + path); return RT_ERR_IO; }
-    const bool ok = std::fwrite(b, 1, buf.size(), f) == buf.size();
+    bool ok = std::fwrite(b, 1, sizeof b, f) == sizeof b;
+    if (rows_bottom_up) {
+        // the frame was stored in BMP row order by the kernel (RT_FRAME_BOTTOM_UP): the pixel array is written as is
+        ok = ok && std::fwrite(bgra, 1, (size_t)row * height, f) == (size_t)row * height;
+    } else {
+        for (int y = 0; y < height && ok; y++) // bottom-up
+            ok = std::fwrite(bgra + (size_t)(height - 1 - y) * row, 1, (size_t)row, f) == (size_t)row;
+    }
     std::fclose(f);
     if (!ok) { rt::set_error("Unable to save BMP buffer to disk"); return RT_ERR_IO; }
     return RT_OK;
+}
+
+extern "C" int rt_write_bmp(const char* path, const uint8_t* bgra, int width, int height)
+{
+    return write_bmp_rows(path, bgra, width, height, false);
+}
+
+extern "C" int rt_write_bmp_bottom_up(const char* path, const uint8_t* bgra, int width, int height)
+{
+    return write_bmp_rows(path, bgra, width, height, true);
 }

@@ -58,6 +58,7 @@ struct RtFrameArgs {
     // camera basis exactly as thread_render derives it (cpu/src/main.c:241-250)
     float pos[3], ul[3], inc_x[3], inc_y[3];
     int   width, height, spp, bounces;
+    int   flip_y;                  // RT_FRAME_BOTTOM_UP: BGRA row y is stored at row height-1-y (BMP order)
     unsigned seed;
     int   tiles_x;                 // tiles per image row
     const unsigned* tile_list;     // tiles this device renders (tile id = ty * tiles_x + tx)

@@ -21,23 +21,30 @@
 
 namespace {
 
+constexpr size_t RT_CTRL_WORDS = 8 + RT_MAX_SMS;
+
 struct Dev {
     int id = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    // second stream: the per-frame statistics copy and (device 0) the device->host copies of finished frames run here, so
+    // that the next frame's kernel never queues behind a copy (one D2H engine serves both: a 32-byte statistics copy in
+    // the render stream was measured to wait ~0.08 ms per frame behind the 8 MB frame copy of the previous frame)
+    cudaStream_t aux = nullptr;
+    // per frame slot: kernel start / kernel end / frame's device work complete (stats copied); ev2: gather (PEER_COPY)
+    cudaEvent_t ev0[RT_FRAME_SLOTS] = {}, ev1[RT_FRAME_SLOTS] = {}, ev_done[RT_FRAME_SLOTS] = {}, ev2 = nullptr;
     // scene (replicated per device)
     float4 *nodes = nullptr, *nodes4 = nullptr, *tris = nullptr, *shade = nullptr, *mats = nullptr, *lights = nullptr;
     int* leaf_cnt = nullptr;
-    // per-frame control block: [0..3] stats (u64), then the tile counter
+    // per-frame control block, one per frame slot (RT_CTRL_WORDS u64 each): [0..3] stats, [4] tile counter, [8..] SM cursors
     unsigned long long* ctrl = nullptr;
-    unsigned long long* ctrl_host = nullptr; // pinned
+    unsigned long long* ctrl_host = nullptr; // pinned, 8 words per frame slot
     // tile list of this device for the current (w, h, parts), row-major: the order tiles are rendered in and
     // the layout of packed tile buffers
     unsigned* tile_list = nullptr;
     int n_tiles = 0;
     size_t tile_cap = 0;
-    // frame storage (device 0 owns the assembled frame; others only in PEER_COPY mode)
+    // local frame of devices > 0 in PEER_COPY mode (the assembled frames live in rt_ctx::slots, on device 0)
     uchar4* bgra = nullptr;
     size_t bgra_px = 0;
     uchar4* packed = nullptr; // packed tiles (gather paths)
@@ -54,11 +61,30 @@ struct Dev {
 
 } // namespace
 
+namespace {
+// One device frame of a frame sequence (RT_FRAME_SLOTS per context, on device 0) and the state of the render queued on it.
+struct Slot {
+    uchar4* bgra = nullptr;
+    size_t bgra_px = 0;
+    uchar4* ipc_frame = nullptr; // another process's frame (CUDA IPC): the peer-store target of this slot's renders
+    int ipc_w = 0, ipc_h = 0;
+    cudaEvent_t copy_done = nullptr;
+    bool render_pending = false, copy_pending = false, rendered = false;
+    int width = 0, height = 0, aov_mask = 0, spp = 0, part_index = 0, part_count = 1, flags = 0;
+    float gather_ms = 0.f;
+    unsigned launches = 0;
+    rt_timing timing{};
+};
+} // namespace
+
 struct rt_ctx {
     std::vector<Dev> devs;
+    Slot slots[RT_FRAME_SLOTS];
+    int last_slot = 0;
+    cudaStream_t copy_stream = nullptr; // device 0: device->host copies of finished frames, overlapping the next render
     RtDeviceScene scene_host_view{}; // n_lights / amb only; pointers are per device
     std::string err;
-    // state of the last render
+    // state of the last finished render (rt_download, rt_packed_tiles, ... refer to it)
     int width = 0, height = 0, aov_mask = 0;
     bool rendered = false;
     int part_index = 0, part_count = 1;
@@ -70,9 +96,6 @@ struct rt_ctx {
     int li_w = 0, li_h = 0, li_parts = 0;
     uchar4* gather_buf = nullptr; // in-process PEER_COPY landing zone on device 0
     size_t gather_px = 0;
-    // imported frame of another process (CUDA IPC)
-    uchar4* ipc_frame = nullptr;
-    int ipc_w = 0, ipc_h = 0;
     size_t scene_bytes = 0;
     int max_depth = 0, stack_need4 = 0;
     // rays per device of the last frame and the shape they belong to (scheduling default, see rt_render)
@@ -218,9 +241,13 @@ void free_dev(Dev& D)
     cudaFree(D.leaf_cnt); cudaFree(D.ctrl); cudaFree(D.tile_list); cudaFree(D.warp_trace);
     cudaFree(D.bgra); cudaFree(D.packed); cudaFree(D.rgb); cudaFree(D.tri_id); cudaFree(D.depth);
     if (D.ctrl_host) cudaFreeHost(D.ctrl_host);
-    if (D.ev0) cudaEventDestroy(D.ev0);
-    if (D.ev1) cudaEventDestroy(D.ev1);
+    for (int s = 0; s < RT_FRAME_SLOTS; s++) {
+        if (D.ev0[s]) cudaEventDestroy(D.ev0[s]);
+        if (D.ev1[s]) cudaEventDestroy(D.ev1[s]);
+        if (D.ev_done[s]) cudaEventDestroy(D.ev_done[s]);
+    }
     if (D.ev2) cudaEventDestroy(D.ev2);
+    if (D.aux) cudaStreamDestroy(D.aux);
     if (D.stream) cudaStreamDestroy(D.stream);
 }
 
@@ -288,7 +315,7 @@ int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** 
     c->scene_host_view.n_lights = (int)flat.n_lights;
     std::memcpy(c->scene_host_view.amb, flat.ambient, 12);
     c->devs.resize(ndev);
-    auto bail = [&](int code) { for (Dev& D : c->devs) free_dev(D); std::string m = c->err; delete c; rt::set_error(m); return code; };
+    auto bail = [&](int code) { std::string m = c->err; rt_destroy(c); rt::set_error(m); return code; };
 #define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { c->err = std::string(#call) + " failed: " + cudaGetErrorString(e__); return bail(RT_ERR_CUDA); } } while (0)
     for (int i = 0; i < ndev; i++) {
         Dev& D = c->devs[i];
@@ -298,7 +325,13 @@ int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** 
         CKC(cudaGetDeviceProperties(&prop, D.id));
         D.sm_count = prop.multiProcessorCount;
         CKC(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
-        CKC(cudaEventCreate(&D.ev0)); CKC(cudaEventCreate(&D.ev1)); CKC(cudaEventCreate(&D.ev2));
+        CKC(cudaStreamCreateWithFlags(&D.aux, cudaStreamNonBlocking));
+        for (int s = 0; s < RT_FRAME_SLOTS; s++) { CKC(cudaEventCreate(&D.ev0[s])); CKC(cudaEventCreate(&D.ev1[s])); CKC(cudaEventCreate(&D.ev_done[s])); }
+        CKC(cudaEventCreate(&D.ev2));
+        if (i == 0) {
+            c->copy_stream = D.aux;
+            for (int s = 0; s < RT_FRAME_SLOTS; s++) CKC(cudaEventCreateWithFlags(&c->slots[s].copy_done, cudaEventDisableTiming));
+        }
         CKC(upload(&D.nodes, flat.nodes.data(), flat.nodes.size() * 4, D.stream));
         CKC(upload(&D.nodes4, flat.nodes4.data(), flat.nodes4.size() * 4, D.stream));
         CKC(upload(&D.tris, flat.tris.data(), flat.tris.size() * 4, D.stream));
@@ -306,8 +339,8 @@ int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** 
         CKC(upload(&D.mats, flat.mats.data(), flat.mats.size() * 4, D.stream));
         CKC(upload(&D.lights, flat.lights.data(), flat.lights.size() * 4, D.stream));
         CKC(upload(&D.leaf_cnt, flat.leaf_cnt.data(), flat.leaf_cnt.size() * 4, D.stream));
-        CKC(cudaMalloc((void**)&D.ctrl, 64 + 8 * RT_MAX_SMS));
-        CKC(cudaMallocHost((void**)&D.ctrl_host, 64));
+        CKC(cudaMalloc((void**)&D.ctrl, 8 * RT_CTRL_WORDS * RT_FRAME_SLOTS));
+        CKC(cudaMallocHost((void**)&D.ctrl_host, 64 * RT_FRAME_SLOTS));
         CKC(cudaStreamSynchronize(D.stream));
         if (i > 0) { // NVLink / NVSwitch peer mapping towards the frame owner
             int can = 0;
@@ -328,31 +361,47 @@ int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** 
 void rt_destroy(rt_ctx* c)
 {
     if (!c) return;
-    if (c->ipc_frame) { cudaSetDevice(c->devs[0].id); cudaIpcCloseMemHandle(c->ipc_frame); }
-    if (!c->devs.empty()) { cudaSetDevice(c->devs[0].id); cudaFree(c->local_index); cudaFree(c->gather_buf); }
+    if (!c->devs.empty()) {
+        cudaSetDevice(c->devs[0].id);
+        cudaDeviceSynchronize();
+        for (Slot& S : c->slots) {
+            if (S.ipc_frame) cudaIpcCloseMemHandle(S.ipc_frame);
+            cudaFree(S.bgra);
+            if (S.copy_done) cudaEventDestroy(S.copy_done);
+        }
+        cudaFree(c->local_index); cudaFree(c->gather_buf);
+    }
     for (Dev& D : c->devs) free_dev(D);
     delete c;
 }
 
-int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
+// Queue one frame on slot p->frame_slot: validation, frame storage, launches on every device, stats copy.  Returns
+// without waiting for the device, except for the unfused RT_GATHER_PEER_COPY assembly, which blocks as before.
+static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
 {
     if (!c || !p) return fail(c, RT_ERR_INVALID, "rt_render: null argument");
     if (p->width < 1 || p->height < 1 || p->width > 65535 || p->height > 32767) return fail(c, RT_ERR_INVALID, "rt_render: bad resolution");
     if (p->spp < 1) return fail(c, RT_ERR_INVALID, "rt_render: spp must be >= 1");
     if (p->bounces > RT_MAX_BOUNCES) return fail(c, RT_ERR_INVALID, "rt_render: bounces > 8");
     if (p->mode != RT_MODE_FAST && p->mode != RT_MODE_STRICT) return fail(c, RT_ERR_INVALID, "rt_render: bad mode");
+    if (p->frame_slot < 0 || p->frame_slot >= RT_FRAME_SLOTS) return fail(c, RT_ERR_INVALID, "rt_render: bad frame_slot");
     const int part_count = p->part_count < 1 ? 1 : p->part_count;
     if (p->part_index < 0 || p->part_index >= part_count) return fail(c, RT_ERR_INVALID, "rt_render: bad partition");
     const int nd = (int)c->devs.size();
     const int w = p->width, h = p->height;
     const size_t npx = (size_t)w * h;
+    const int slot = p->frame_slot;
+    Slot& S = c->slots[slot];
+    if (S.render_pending) return fail(c, RT_ERR_STATE, "rt_render_async: a render is still queued on this frame slot (call rt_frame_wait first)");
     int gather = p->gather;
     for (int d = 1; d < nd; d++)
         if (!c->devs[d].peer_to_0) gather = RT_GATHER_PEER_COPY; // no NVLink mapping: staged copies
     if (nd > 1 && gather == RT_GATHER_PEER_COPY && (p->aov_mask & (RT_AOV_RGB_F32 | RT_AOV_TRI_ID | RT_AOV_DEPTH)))
         for (int d = 1; d < nd; d++)
             if (!c->devs[d].peer_to_0) return fail(c, RT_ERR_INVALID, "rt_render: AOVs on several devices need peer access");
-    if (c->ipc_frame && (c->ipc_w != w || c->ipc_h != h)) return fail(c, RT_ERR_STATE, "rt_render: imported frame has another size");
+    if (nd > 1 && gather == RT_GATHER_PEER_COPY && (p->frame_flags & RT_FRAME_BOTTOM_UP))
+        return fail(c, RT_ERR_INVALID, "rt_render: RT_FRAME_BOTTOM_UP is not available with RT_GATHER_PEER_COPY");
+    if (S.ipc_frame && (S.ipc_w != w || S.ipc_h != h)) return fail(c, RT_ERR_STATE, "rt_render: imported frame has another size");
     if (nd > 1 && part_count > 1) return fail(c, RT_ERR_INVALID, "rt_render: use either several devices per context or part_count > 1");
 
     int rc = setup_tiles(c, w, h, p->part_index, part_count);
@@ -361,7 +410,7 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
     // frame storage on device 0 (+ local frames for PEER_COPY)
     Dev& D0 = c->devs[0];
     CK(c, cudaSetDevice(D0.id));
-    if ((rc = ensure(c, &D0.bgra, &D0.bgra_px, npx))) return rc;
+    if ((rc = ensure(c, &S.bgra, &S.bgra_px, npx))) return rc;
     if (p->aov_mask & RT_AOV_RGB_F32) { if ((rc = ensure(c, &D0.rgb, &D0.aov_px[0], 3 * npx))) return rc; }
     if (p->aov_mask & RT_AOV_TRI_ID) { if ((rc = ensure(c, &D0.tri_id, &D0.aov_px[1], npx))) return rc; }
     if (p->aov_mask & RT_AOV_DEPTH) { if ((rc = ensure(c, &D0.depth, &D0.aov_px[2], npx))) return rc; }
@@ -382,6 +431,7 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
     std::memcpy(fa.pos, cb.pos, 12); std::memcpy(fa.ul, cb.ul, 12);
     std::memcpy(fa.inc_x, cb.inc_x, 12); std::memcpy(fa.inc_y, cb.inc_y, 12);
     fa.width = w; fa.height = h; fa.spp = p->spp; fa.bounces = p->bounces; fa.seed = p->seed;
+    fa.flip_y = (p->frame_flags & RT_FRAME_BOTTOM_UP) ? 1 : 0;
     fa.tiles_x = tiles_x_of(w);
 
     RtLaunchCfg cfg;
@@ -401,24 +451,40 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
     cfg.wide = want_wide && c->stack_need4 <= RT_STACK_ENTRIES_WIDE;
     fa.refill_threshold = p->refill_threshold > 0 ? std::min(p->refill_threshold, 32) : 20;
 
-    unsigned launches = 0;
+    S.width = w; S.height = h; S.aov_mask = p->aov_mask; S.spp = p->spp; S.flags = p->frame_flags;
+    S.part_index = p->part_index; S.part_count = part_count;
+    S.gather_ms = 0.f; S.launches = 0;
+    uchar4* const target = S.ipc_frame ? S.ipc_frame : S.bgra;
+
     if (p->bounces <= 0) {
         // BOUNCES == 0: raytrace returns black before any traversal (cpu/src/raytracer.c:104-105)
         CK(c, cudaSetDevice(D0.id));
-        uchar4* target = c->ipc_frame ? c->ipc_frame : D0.bgra;
-        fill_bgra_kernel<<<D0.sm_count * 4, 256, 0, D0.stream>>>(target, npx, make_uchar4(0, 0, 0, 255));
-        CK(c, cudaGetLastError());
-        if (p->aov_mask & RT_AOV_RGB_F32) CK(c, cudaMemsetAsync(D0.rgb, 0, 12 * npx, D0.stream));
-        if (p->aov_mask & RT_AOV_TRI_ID) CK(c, cudaMemsetAsync(D0.tri_id, 0xff, 4 * npx, D0.stream));
-        if (p->aov_mask & RT_AOV_DEPTH) CK(c, cudaMemsetAsync(D0.depth, 0, 4 * npx, D0.stream));
-        CK(c, cudaStreamSynchronize(D0.stream));
-        if (tm) { std::memset(tm, 0, sizeof *tm); tm->launches = 1; tm->n_devices = nd; }
-        c->width = w; c->height = h; c->aov_mask = p->aov_mask; c->rendered = true;
-        c->part_index = p->part_index; c->part_count = part_count;
+        if (S.copy_pending) CK(c, cudaStreamWaitEvent(D0.stream, S.copy_done, 0));
+        for (int d = 0; d < nd; d++) { // other devices have nothing to do: their events only mark "complete"
+            Dev& D = c->devs[d];
+            CK(c, cudaSetDevice(D.id));
+            unsigned long long* const ctrl = D.ctrl + RT_CTRL_WORDS * slot;
+            CK(c, cudaMemsetAsync(ctrl, 0, 8 * RT_CTRL_WORDS, D.stream));
+            CK(c, cudaEventRecord(D.ev0[slot], D.stream));
+            if (d == 0) {
+                fill_bgra_kernel<<<D0.sm_count * 4, 256, 0, D0.stream>>>(target, npx, make_uchar4(0, 0, 0, 255));
+                CK(c, cudaGetLastError());
+                if (p->aov_mask & RT_AOV_RGB_F32) CK(c, cudaMemsetAsync(D0.rgb, 0, 12 * npx, D0.stream));
+                if (p->aov_mask & RT_AOV_TRI_ID) CK(c, cudaMemsetAsync(D0.tri_id, 0xff, 4 * npx, D0.stream));
+                if (p->aov_mask & RT_AOV_DEPTH) CK(c, cudaMemsetAsync(D0.depth, 0, 4 * npx, D0.stream));
+            }
+            CK(c, cudaEventRecord(D.ev1[slot], D.stream));
+            CK(c, cudaStreamWaitEvent(D.aux, D.ev1[slot], 0));
+            CK(c, cudaMemcpyAsync(D.ctrl_host + 8 * slot, ctrl, 32, cudaMemcpyDeviceToHost, D.aux));
+            CK(c, cudaEventRecord(D.ev_done[slot], D.aux));
+        }
+        S.launches = 1;
+        S.render_pending = true;
         return RT_OK;
     }
 
     // ---- launch on every device ----
+    unsigned launches = 0;
     for (int d = 0; d < nd; d++) {
         Dev& D = c->devs[d];
         CK(c, cudaSetDevice(D.id));
@@ -427,11 +493,12 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
         sc.mats = D.mats; sc.lights = D.lights; sc.leaf_cnt = D.leaf_cnt;
         RtFrameArgs f = fa;
         f.tile_list = D.tile_list; f.n_tiles = D.n_tiles;
-        f.stats = D.ctrl; f.tile_counter = reinterpret_cast<unsigned*>(D.ctrl + 4);
-        f.sm_cursor = small_frame ? nullptr : D.ctrl + 8; // SM-local work queues pay off on throughput-bound frames only
+        unsigned long long* const ctrl = D.ctrl + RT_CTRL_WORDS * slot;
+        f.stats = ctrl; f.tile_counter = reinterpret_cast<unsigned*>(ctrl + 4);
+        f.sm_cursor = small_frame ? nullptr : ctrl + 8; // SM-local work queues pay off on throughput-bound frames only
         f.n_sms = (unsigned)std::min(D.sm_count, RT_MAX_SMS);
         const bool local = (d > 0 && gather == RT_GATHER_PEER_COPY);
-        f.bgra = local ? D.bgra : (c->ipc_frame ? c->ipc_frame : D0.bgra); // peer-mapped for d > 0
+        f.bgra = local ? D.bgra : target; // peer-mapped for d > 0
         f.rgb = (p->aov_mask & RT_AOV_RGB_F32) ? D0.rgb : nullptr;
         f.tri_id = (p->aov_mask & RT_AOV_TRI_ID) ? D0.tri_id : nullptr;
         f.depth = (p->aov_mask & RT_AOV_DEPTH) ? D0.depth : nullptr;
@@ -455,16 +522,23 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
             f.warp_trace = D.warp_trace;
             D.warp_trace_n = (int)nw;
         }
-        CK(c, cudaMemsetAsync(D.ctrl, 0, 64 + 8 * RT_MAX_SMS, D.stream));
-        CK(c, cudaEventRecord(D.ev0, D.stream));
+        // a copy of this slot's previous frame that is still in flight must finish before its pixels are overwritten
+        if (S.copy_pending) CK(c, cudaStreamWaitEvent(D.stream, S.copy_done, 0));
+        CK(c, cudaMemsetAsync(ctrl, 0, 8 * RT_CTRL_WORDS, D.stream));
+        CK(c, cudaEventRecord(D.ev0[slot], D.stream));
         e = (p->mode == RT_MODE_STRICT) ? rt_launch_strict(sc, f, cf, D.stream) : rt_launch_fast(sc, f, cf, D.stream);
         CK(c, e);
         launches++;
-        CK(c, cudaEventRecord(D.ev1, D.stream));
-        CK(c, cudaMemcpyAsync(D.ctrl_host, D.ctrl, 32, cudaMemcpyDeviceToHost, D.stream));
+        CK(c, cudaEventRecord(D.ev1[slot], D.stream));
+        // statistics -> pinned host memory on the second stream (this slot's control block is not touched again before
+        // the slot has been waited on, so the next frame's kernel does not depend on this copy)
+        CK(c, cudaStreamWaitEvent(D.aux, D.ev1[slot], 0));
+        CK(c, cudaMemcpyAsync(D.ctrl_host + 8 * slot, ctrl, 32, cudaMemcpyDeviceToHost, D.aux));
+        CK(c, cudaEventRecord(D.ev_done[slot], D.aux));
     }
+    S.render_pending = true;
 
-    // ---- unfused gather: pack on each device, copy to device 0, unpack ----
+    // ---- unfused gather: pack on each device, copy to device 0, unpack (blocking) ----
     float gather_ms = 0.f;
     if (nd > 1 && gather == RT_GATHER_PEER_COPY) {
         const int parts = part_count * nd;
@@ -492,14 +566,14 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
         // device 0's own tiles are already in place; scatter the others (device 0's slot is skipped by
         // packing its own tiles too, which keeps the unpack kernel branch-free)
         if (D0.n_tiles) {
-            pack_tiles_kernel<<<D0.n_tiles, RT_TILE_PIXELS, 0, D0.stream>>>(D0.bgra, D0.packed, D0.tile_list, D0.n_tiles, fa.tiles_x, w, h);
+            pack_tiles_kernel<<<D0.n_tiles, RT_TILE_PIXELS, 0, D0.stream>>>(S.bgra, D0.packed, D0.tile_list, D0.n_tiles, fa.tiles_x, w, h);
             CK(c, cudaGetLastError());
             launches++;
             CK(c, cudaMemcpyAsync(c->gather_buf + stride * (size_t)(p->part_index * nd), D0.packed, (size_t)D0.n_tiles * RT_TILE_PIXELS * 4,
                                   cudaMemcpyDeviceToDevice, D0.stream));
         }
         dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
-        unpack_tiles_kernel<<<grd, blk, 0, D0.stream>>>(D0.bgra, c->gather_buf, stride, c->local_index, parts, fa.tiles_x, w, h);
+        unpack_tiles_kernel<<<grd, blk, 0, D0.stream>>>(S.bgra, c->gather_buf, stride, c->local_index, parts, fa.tiles_x, w, h);
         CK(c, cudaGetLastError());
         launches++;
         cudaEvent_t done;
@@ -514,37 +588,102 @@ int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
             float t_d = 0.f;
             CK(c, cudaSetDevice(c->devs[d].id));
             CK(c, cudaEventSynchronize(c->devs[d].ev2));
-            CK(c, cudaEventElapsedTime(&t_d, c->devs[d].ev1, c->devs[d].ev2));
+            CK(c, cudaEventElapsedTime(&t_d, c->devs[d].ev1[slot], c->devs[d].ev2));
             worst = std::max(worst, t_d);
         }
         gather_ms += worst;
     }
-
-    // ---- completion + timing ----
-    rt_timing t;
-    std::memset(&t, 0, sizeof t);
-    float kmax = 0.f;
-    for (int d = 0; d < nd; d++) {
-        Dev& D = c->devs[d];
-        CK(c, cudaSetDevice(D.id));
-        CK(c, cudaStreamSynchronize(D.stream));
-        CK(c, cudaEventElapsedTime(&t.kernel_ms[d], D.ev0, D.ev1));
-        kmax = std::max(kmax, t.kernel_ms[d]);
-        t.rays_closest += D.ctrl_host[0];
-        t.rays_shadow += D.ctrl_host[1];
-        t.inner_visits += D.ctrl_host[2];
-        t.tri_tests += D.ctrl_host[3];
-    }
-    c->rays_per_dev = (double)(t.rays_closest + t.rays_shadow) / nd;
-    c->rays_w = w; c->rays_h = h; c->rays_spp = p->spp; c->rays_parts = part_count;
-    t.gather_ms = gather_ms;
-    t.total_ms = kmax + gather_ms;
-    t.launches = launches;
-    t.n_devices = (uint32_t)nd;
-    if (tm) *tm = t;
-    c->width = w; c->height = h; c->aov_mask = p->aov_mask; c->rendered = true;
-    c->part_index = p->part_index; c->part_count = part_count;
+    S.gather_ms = gather_ms;
+    S.launches = launches;
     return RT_OK;
+}
+
+// Wait for everything queued on the slot (render, then a device->host copy if one was queued); timing of its render.
+static int finish_frame(rt_ctx* c, int slot, rt_timing* tm)
+{
+    if (!c) return fail(c, RT_ERR_INVALID, "rt_frame_wait: null context");
+    if (slot < 0 || slot >= RT_FRAME_SLOTS) return fail(c, RT_ERR_INVALID, "rt_frame_wait: bad frame slot");
+    Slot& S = c->slots[slot];
+    if (!S.render_pending && !S.rendered) return fail(c, RT_ERR_STATE, "rt_frame_wait: nothing was rendered on this frame slot");
+    const int nd = (int)c->devs.size();
+    if (S.render_pending) {
+        rt_timing t;
+        std::memset(&t, 0, sizeof t);
+        float kmax = 0.f;
+        for (int d = 0; d < nd; d++) {
+            Dev& D = c->devs[d];
+            CK(c, cudaSetDevice(D.id));
+            CK(c, cudaEventSynchronize(D.ev_done[slot]));
+            CK(c, cudaEventElapsedTime(&t.kernel_ms[d], D.ev0[slot], D.ev1[slot]));
+            kmax = std::max(kmax, t.kernel_ms[d]);
+            const unsigned long long* st = D.ctrl_host + 8 * slot;
+            t.rays_closest += st[0];
+            t.rays_shadow += st[1];
+            t.inner_visits += st[2];
+            t.tri_tests += st[3];
+        }
+        c->rays_per_dev = (double)(t.rays_closest + t.rays_shadow) / nd;
+        c->rays_w = S.width; c->rays_h = S.height; c->rays_spp = S.spp; c->rays_parts = S.part_count;
+        t.gather_ms = S.gather_ms;
+        t.total_ms = kmax + S.gather_ms;
+        t.launches = S.launches;
+        t.n_devices = (uint32_t)nd;
+        S.timing = t;
+        S.render_pending = false;
+        S.rendered = true;
+        c->width = S.width; c->height = S.height; c->aov_mask = S.aov_mask; c->rendered = true;
+        c->part_index = S.part_index; c->part_count = S.part_count;
+        c->last_slot = slot;
+    }
+    if (S.copy_pending) {
+        CK(c, cudaSetDevice(c->devs[0].id));
+        CK(c, cudaEventSynchronize(S.copy_done));
+        S.copy_pending = false;
+    }
+    if (tm) *tm = S.timing;
+    return RT_OK;
+}
+
+int rt_render_async(rt_ctx* c, const rt_render_params* p) { return enqueue_frame(c, p); }
+
+int rt_frame_wait(rt_ctx* c, int slot, rt_timing* tm) { return finish_frame(c, slot, tm); }
+
+int rt_render(rt_ctx* c, const rt_render_params* p, rt_timing* tm)
+{
+    int rc = enqueue_frame(c, p);
+    if (rc) return rc;
+    return finish_frame(c, p->frame_slot, tm);
+}
+
+int rt_download_async(rt_ctx* c, int slot, uint8_t* host_bgra)
+{
+    if (!c || !host_bgra) return fail(c, RT_ERR_INVALID, "rt_download_async: null argument");
+    if (slot < 0 || slot >= RT_FRAME_SLOTS) return fail(c, RT_ERR_INVALID, "rt_download_async: bad frame slot");
+    Slot& S = c->slots[slot];
+    if (!S.render_pending && !S.rendered) return fail(c, RT_ERR_STATE, "rt_download_async: nothing was rendered on this frame slot");
+    Dev& D0 = c->devs[0];
+    CK(c, cudaSetDevice(D0.id));
+    // the copy is ordered after the slot's render kernel on EVERY device (peer stores land in this frame)
+    for (Dev& D : c->devs) CK(c, cudaStreamWaitEvent(c->copy_stream, D.ev1[slot], 0));
+    CK(c, cudaMemcpyAsync(host_bgra, S.ipc_frame ? S.ipc_frame : S.bgra, (size_t)S.width * S.height * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+    CK(c, cudaEventRecord(S.copy_done, c->copy_stream));
+    S.copy_pending = true;
+    return RT_OK;
+}
+
+int rt_host_alloc(size_t bytes, void** out)
+{
+    if (!out || !bytes) return fail(nullptr, RT_ERR_INVALID, "rt_host_alloc: bad argument");
+    *out = nullptr;
+    if (rt_device_count() <= 0) return fail(nullptr, RT_ERR_NO_DEVICE, "rt_host_alloc: no CUDA device");
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, RT_ERR_NOMEM, std::string("rt_host_alloc: ") + cudaGetErrorString(e)); }
+    return RT_OK;
+}
+
+void rt_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
 }
 
 int rt_download(rt_ctx* c, uint8_t* bgra, float* rgb, int32_t* tri_id, float* depth_t)
@@ -552,12 +691,13 @@ int rt_download(rt_ctx* c, uint8_t* bgra, float* rgb, int32_t* tri_id, float* de
     if (!c) return fail(c, RT_ERR_INVALID, "rt_download: null context");
     if (!c->rendered) return fail(c, RT_ERR_STATE, "rt_download: nothing rendered yet");
     Dev& D0 = c->devs[0];
+    Slot& S = c->slots[c->last_slot];
     const size_t npx = (size_t)c->width * c->height;
     CK(c, cudaSetDevice(D0.id));
     if (rgb && !(c->aov_mask & RT_AOV_RGB_F32)) return fail(c, RT_ERR_STATE, "rt_download: RT_AOV_RGB_F32 was not rendered");
     if (tri_id && !(c->aov_mask & RT_AOV_TRI_ID)) return fail(c, RT_ERR_STATE, "rt_download: RT_AOV_TRI_ID was not rendered");
     if (depth_t && !(c->aov_mask & RT_AOV_DEPTH)) return fail(c, RT_ERR_STATE, "rt_download: RT_AOV_DEPTH was not rendered");
-    if (bgra) CK(c, cudaMemcpyAsync(bgra, c->ipc_frame ? c->ipc_frame : D0.bgra, npx * 4, cudaMemcpyDeviceToHost, D0.stream));
+    if (bgra) CK(c, cudaMemcpyAsync(bgra, S.ipc_frame ? S.ipc_frame : S.bgra, npx * 4, cudaMemcpyDeviceToHost, D0.stream));
     if (rgb) CK(c, cudaMemcpyAsync(rgb, D0.rgb, npx * 12, cudaMemcpyDeviceToHost, D0.stream));
     if (tri_id) CK(c, cudaMemcpyAsync(tri_id, D0.tri_id, npx * 4, cudaMemcpyDeviceToHost, D0.stream));
     if (depth_t) CK(c, cudaMemcpyAsync(depth_t, D0.depth, npx * 4, cudaMemcpyDeviceToHost, D0.stream));
@@ -569,7 +709,7 @@ int rt_frame_device_ptr(rt_ctx* c, void** dev_ptr, size_t* bytes)
 {
     if (!c || !dev_ptr) return fail(c, RT_ERR_INVALID, "rt_frame_device_ptr: null argument");
     if (!c->rendered) return fail(c, RT_ERR_STATE, "rt_frame_device_ptr: nothing rendered yet");
-    *dev_ptr = c->ipc_frame ? c->ipc_frame : c->devs[0].bgra;
+    { Slot& S = c->slots[c->last_slot]; *dev_ptr = S.ipc_frame ? S.ipc_frame : S.bgra; }
     if (bytes) *bytes = (size_t)c->width * c->height * 4;
     return RT_OK;
 }
@@ -580,11 +720,13 @@ int rt_packed_tiles(rt_ctx* c, void** dev_ptr, size_t* bytes)
     if (!c->rendered) return fail(c, RT_ERR_STATE, "rt_packed_tiles: nothing rendered yet");
     if (c->devs.size() != 1) return fail(c, RT_ERR_STATE, "rt_packed_tiles: one device per context expected");
     Dev& D = c->devs[0];
+    Slot& S = c->slots[c->last_slot];
+    if (S.flags & RT_FRAME_BOTTOM_UP) return fail(c, RT_ERR_STATE, "rt_packed_tiles: the last frame was rendered bottom-up");
     CK(c, cudaSetDevice(D.id));
     int rc = ensure(c, &D.packed, &D.packed_px, std::max<size_t>((size_t)D.n_tiles * RT_TILE_PIXELS, 1));
     if (rc) return rc;
     if (D.n_tiles) {
-        pack_tiles_kernel<<<D.n_tiles, RT_TILE_PIXELS, 0, D.stream>>>(D.bgra, D.packed, D.tile_list, D.n_tiles, tiles_x_of(c->width), c->width, c->height);
+        pack_tiles_kernel<<<D.n_tiles, RT_TILE_PIXELS, 0, D.stream>>>(S.bgra, D.packed, D.tile_list, D.n_tiles, tiles_x_of(c->width), c->width, c->height);
         CK(c, cudaGetLastError());
     }
     CK(c, cudaStreamSynchronize(D.stream));
@@ -603,7 +745,7 @@ int rt_unpack_tiles(rt_ctx* c, const void* dev_gathered, size_t stride_bytes, in
     if (rc) return rc;
     CK(c, cudaSetDevice(D0.id));
     dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
-    unpack_tiles_kernel<<<grd, blk, 0, D0.stream>>>(D0.bgra, static_cast<const uchar4*>(dev_gathered), stride_bytes / 4, c->local_index,
+    unpack_tiles_kernel<<<grd, blk, 0, D0.stream>>>(c->slots[c->last_slot].bgra, static_cast<const uchar4*>(dev_gathered), stride_bytes / 4, c->local_index,
                                                     part_count, tiles_x_of(w), w, h);
     CK(c, cudaGetLastError());
     CK(c, cudaStreamSynchronize(D0.stream));
@@ -627,33 +769,50 @@ int rt_debug_warp_trace(rt_ctx* c, int enable, unsigned long long* out, int max_
     return n;
 }
 
-int rt_frame_ipc_export(rt_ctx* c, int width, int height, void* handle64)
+// Diagnostics: replace device 0's tile order for the current frame shape (the tile list must already exist, i.e. a frame
+// of that shape was rendered) — experiments with cost-ordered scheduling.
+int rt_debug_set_tile_order(rt_ctx* c, const unsigned* tiles, int n)
 {
-    if (!c || !handle64 || width < 1 || height < 1) return fail(c, RT_ERR_INVALID, "rt_frame_ipc_export: bad argument");
+    if (!c || !tiles) return RT_ERR_INVALID;
+    Dev& D = c->devs[0];
+    if (n != D.n_tiles) return fail(c, RT_ERR_INVALID, "rt_debug_set_tile_order: tile count differs from the current tile list");
+    CK(c, cudaSetDevice(D.id));
+    CK(c, cudaMemcpy(D.tile_list, tiles, (size_t)n * 4, cudaMemcpyHostToDevice));
+    return RT_OK;
+}
+
+int rt_frame_ipc_export_slot(rt_ctx* c, int slot, int width, int height, void* handle64)
+{
+    if (!c || !handle64 || width < 1 || height < 1 || slot < 0 || slot >= RT_FRAME_SLOTS) return fail(c, RT_ERR_INVALID, "rt_frame_ipc_export: bad argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     Dev& D0 = c->devs[0];
+    Slot& S = c->slots[slot];
     CK(c, cudaSetDevice(D0.id));
-    int rc = ensure(c, &D0.bgra, &D0.bgra_px, (size_t)width * height);
+    int rc = ensure(c, &S.bgra, &S.bgra_px, (size_t)width * height);
     if (rc) return rc;
     cudaIpcMemHandle_t hnd;
-    CK(c, cudaIpcGetMemHandle(&hnd, D0.bgra));
+    CK(c, cudaIpcGetMemHandle(&hnd, S.bgra));
     std::memcpy(handle64, &hnd, 64);
     return RT_OK;
 }
 
-int rt_frame_ipc_import(rt_ctx* c, const void* handle64, int width, int height)
+int rt_frame_ipc_import_slot(rt_ctx* c, int slot, const void* handle64, int width, int height)
 {
-    if (!c || !handle64 || width < 1 || height < 1) return fail(c, RT_ERR_INVALID, "rt_frame_ipc_import: bad argument");
+    if (!c || !handle64 || width < 1 || height < 1 || slot < 0 || slot >= RT_FRAME_SLOTS) return fail(c, RT_ERR_INVALID, "rt_frame_ipc_import: bad argument");
     Dev& D0 = c->devs[0];
+    Slot& S = c->slots[slot];
     CK(c, cudaSetDevice(D0.id));
-    if (c->ipc_frame) { CK(c, cudaIpcCloseMemHandle(c->ipc_frame)); c->ipc_frame = nullptr; }
+    if (S.ipc_frame) { CK(c, cudaIpcCloseMemHandle(S.ipc_frame)); S.ipc_frame = nullptr; }
     cudaIpcMemHandle_t hnd;
     std::memcpy(&hnd, handle64, 64);
     void* p = nullptr;
     CK(c, cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
-    c->ipc_frame = static_cast<uchar4*>(p);
-    c->ipc_w = width; c->ipc_h = height;
+    S.ipc_frame = static_cast<uchar4*>(p);
+    S.ipc_w = width; S.ipc_h = height;
     return RT_OK;
 }
+
+int rt_frame_ipc_export(rt_ctx* c, int width, int height, void* handle64) { return rt_frame_ipc_export_slot(c, 0, width, height, handle64); }
+int rt_frame_ipc_import(rt_ctx* c, const void* handle64, int width, int height) { return rt_frame_ipc_import_slot(c, 0, handle64, width, height); }
 
 } // extern "C"

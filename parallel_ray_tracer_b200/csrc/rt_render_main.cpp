@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -17,13 +18,17 @@ static void usage()
 {
     std::printf("usage: rt_render (--scene-dir DIR | --rtsc FILE | --soup N) [--width W] [--height H] [--spp S] [--seed K]\n"
                 "                 [--bounces B] [--heuristic 6|0|1] [--refbin-tree] [--strict] [--gpus N] [--iterations I] [--warmup W]\n"
-                "                 [--cam px py pz rx ry rz fov] [--out FILE.bmp] [--ctas-per-sm C] [--block T] [--refill R] [--peer-copy]\n");
+                "                 [--cam px py pz rx ry rz fov] [--out FILE.bmp] [--ctas-per-sm C] [--block T] [--refill R] [--peer-copy]\n"
+                "                 [--sequence N [--spin DZ]]   N frames end to end (camera rot.z += DZ per frame), each copied to the host\n"
+                "                                              while the next one renders; the last one is written bottom-up as the BMP\n");
 }
 
 int main(int argc, char** argv)
 {
     const char *scene_dir = nullptr, *rtsc = nullptr, *out = "render.bmp";
     int soup = 0, heuristic = 6, gpus = 1, iterations = 100, warmup = 50; // gpu/include/options.cuh:25-26
+    int sequence = 0;
+    float spin = 0.0f;
     rt_render_params p;
     rt_render_params_default(&p);
     for (int i = 1; i < argc; i++) {
@@ -48,6 +53,8 @@ int main(int argc, char** argv)
         else if (a == "--block") p.block_threads = std::atoi(next());
         else if (a == "--refill") p.refill_threshold = std::atoi(next());
         else if (a == "--peer-copy") p.gather = RT_GATHER_PEER_COPY;
+        else if (a == "--sequence") sequence = std::atoi(next());
+        else if (a == "--spin") spin = (float)std::atof(next());
         else if (a == "--cam") {
             for (int k = 0; k < 3; k++) p.cam.pos[k] = (float)std::atof(next());
             for (int k = 0; k < 3; k++) p.cam.rot[k] = (float)std::atof(next());
@@ -103,6 +110,39 @@ int main(int argc, char** argv)
         std::printf("Frame time (median): %.3f ms\nFrame time (stddev): %.3f ms^2\nExpected FPS: %.3f\n", median, sd, 1000 / mean);
         std::printf("Rays per frame: %.0f (closest %llu, shadow %llu)\nMrays/s (median frame): %.1f\n", rays,
                     (unsigned long long)tm.rays_closest, (unsigned long long)tm.rays_shadow, rays / median / 1e3);
+    }
+    if (sequence > 0) {
+        // Frame sequence, end to end (cpu/src/main.c:169-185 with the moving camera of :107): frame k renders into frame
+        // slot k % 2 while frame k-1 is copied into pinned host memory; rows are stored bottom-up by the kernel, so the
+        // last host buffer is written as the BMP pixel array without a flip.
+        void* host[RT_FRAME_SLOTS] = {nullptr, nullptr};
+        const size_t bytes = (size_t)p.width * p.height * 4;
+        for (int s = 0; s < RT_FRAME_SLOTS; s++)
+            if ((rc = rt_host_alloc(bytes, &host[s]))) { std::fprintf(stderr, "%s\n", rt_last_error(nullptr)); return 1; }
+        rt_render_params q = p;
+        q.frame_flags |= RT_FRAME_BOTTOM_UP;
+        if (q.gather == RT_GATHER_PEER_COPY) { std::fprintf(stderr, "--sequence needs the fused gather\n"); return 2; }
+        struct timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        for (int k = 0; k < sequence; k++) {
+            const int s = k % RT_FRAME_SLOTS;
+            if (k >= RT_FRAME_SLOTS && (rc = rt_frame_wait(ctx, s, nullptr))) { std::fprintf(stderr, "%s\n", rt_last_error(ctx)); return 1; }
+            q.frame_slot = s;
+            q.cam.rot[2] = p.cam.rot[2] + spin * (float)k;
+            if ((rc = rt_render_async(ctx, &q)) || (rc = rt_download_async(ctx, s, (uint8_t*)host[s]))) { std::fprintf(stderr, "%s\n", rt_last_error(ctx)); return 1; }
+        }
+        for (int s = 0; s < RT_FRAME_SLOTS && s < sequence; s++)
+            if ((rc = rt_frame_wait(ctx, s, nullptr))) { std::fprintf(stderr, "%s\n", rt_last_error(ctx)); return 1; }
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        const double ms = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) / 1e6;
+        std::printf("\n# Sequence #\n%d frames rendered and copied to the host in %.3f ms: %.3f ms per frame, %.1f FPS end to end\n", sequence, ms,
+                    ms / sequence, 1000.0 * sequence / ms);
+        std::string seq_out = std::string(out) + ".last.bmp";
+        if (rt_write_bmp_bottom_up(seq_out.c_str(), (const uint8_t*)host[(sequence - 1) % RT_FRAME_SLOTS], p.width, p.height)) {
+            std::fprintf(stderr, "%s\n", rt_last_error(nullptr));
+            return 1;
+        }
+        for (int s = 0; s < RT_FRAME_SLOTS; s++) rt_host_free(host[s]);
     }
     rt_destroy(ctx);
     rt_scene_free(sc);

@@ -256,9 +256,11 @@ def test_cpp_host_driver_writes_the_reference_bmp(rt, oracle_scenes, tmp_path):
         pytest.skip("rt_render not built")
     out = tmp_path / "o.bmp"
     r = subprocess.run([str(exe), "--rtsc", str(O.HERE.parent / "tests" / "golden" / "scenes" / "car_only.rtsc"), "--width", "320", "--height", "180",
-                        "--strict", "--iterations", "3", "--warmup", "1", "--out", str(out)], capture_output=True, text=True, timeout=300)
+                        "--strict", "--iterations", "3", "--warmup", "1", "--out", str(out), "--sequence", "5"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "Frame time (median)" in r.stdout and "Mrays/s" in r.stdout
+    assert "Frame time (median)" in r.stdout and "Mrays/s" in r.stdout and "FPS end to end" in r.stdout
+    # the sequence mode's last frame (kernel-written bottom-up rows, no host flip) is the same file
+    assert (tmp_path / "o.bmp.last.bmp").read_bytes() == out.read_bytes()
     raw = out.read_bytes()
     assert len(raw) == 54 + 4 * 320 * 180 and raw[:2] == b"BM"
     rows = np.frombuffer(raw, np.uint8, 4 * 320 * 180, 54).reshape(180, 320, 4)[::-1]
