@@ -106,6 +106,18 @@ int rt_scene_instance_grid(const rt_scene* base, uint32_t nx, uint32_t ny, uint3
  * does not depend on which is used).  See csrc/bvh_build.cpp. */
 #define RT_BVH_REFBIN 0x100
 int rt_scene_build_bvh(rt_scene* s, int heuristic);
+/* The same tree built on a GPU (csrc/bvh_build_gpu.cu): heuristic 6 only (optionally | RT_BVH_REFBIN), node for node
+ * and tri_idx entry for entry the result of rt_scene_build_bvh.  Degenerate inputs that trip the reference's
+ * bvh_len >= 2N guard (cpu/src/bvh.c:80-83) are handed to the host builder (stats->fell_back = 1). */
+typedef struct rt_bvh_gpu_stats {
+    float    total_ms, upload_ms, top_ms, subtree_ms, assemble_ms, download_ms;
+    int32_t  levels;     /* level-synchronous passes over the top of the tree */
+    int32_t  top_nodes;  /* nodes created by those passes */
+    int32_t  subtrees;   /* subtrees finished by one thread each */
+    int32_t  fell_back;
+    uint32_t nodes;      /* bvh_len */
+} rt_bvh_gpu_stats;
+int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt_bvh_gpu_stats* stats_out);
 /* Fill a borrowed view (valid until the scene is changed or freed). */
 int rt_scene_view(const rt_scene* s, rt_scene_desc* out);
 void rt_scene_free(rt_scene* s);

@@ -45,7 +45,7 @@ EXPORTS = [
     "rt_part_tile_count", "rt_packed_tiles", "rt_unpack_tiles", "rt_frame_ipc_export", "rt_frame_ipc_import",
     "rt_frame_device_ptr", "rt_write_bmp", "rt_abi_version", "rt_device_count", "rt_debug_warp_trace",
     "rt_render_async", "rt_download_async", "rt_frame_wait", "rt_host_alloc", "rt_host_free",
-    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order",
+    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order", "rt_scene_build_bvh_gpu",
 ]
 
 
@@ -84,6 +84,12 @@ class rt_timing(C.Structure):
                 ("tri_tests", C.c_uint64), ("launches", C.c_uint32), ("n_devices", C.c_uint32)]
 
 
+class rt_bvh_gpu_stats(C.Structure):
+    _fields_ = [("total_ms", C.c_float), ("upload_ms", C.c_float), ("top_ms", C.c_float), ("subtree_ms", C.c_float),
+                ("assemble_ms", C.c_float), ("download_ms", C.c_float), ("levels", C.c_int32), ("top_nodes", C.c_int32),
+                ("subtrees", C.c_int32), ("fell_back", C.c_int32), ("nodes", C.c_uint32)]
+
+
 def build(verbose: bool = False) -> Path:
     """Compile csrc/ for sm_100a into librt_b200.so (in-tree; nvcc cross-compiles without a GPU)."""
     r = subprocess.run(["make", "-C", str(PKG_DIR / "csrc"), "-j", str(os.cpu_count() or 4)], capture_output=True, text=True)
@@ -115,6 +121,7 @@ def lib() -> C.CDLL:
     L.rt_scene_soup.argtypes = [u32, u32, C.POINTER(vp)]
     L.rt_scene_instance_grid.argtypes = [vp, u32, u32, u32, C.POINTER(C.c_float), u32, C.POINTER(vp)]
     L.rt_scene_build_bvh.argtypes = [vp, i32]
+    L.rt_scene_build_bvh_gpu.argtypes = [vp, i32, i32, C.POINTER(rt_bvh_gpu_stats)]
     L.rt_scene_view.argtypes = [vp, C.POINTER(rt_scene_desc)]
     L.rt_scene_free.argtypes = [vp]; L.rt_scene_free.restype = None
     L.rt_render_params_default.argtypes = [C.POINTER(rt_render_params)]; L.rt_render_params_default.restype = None
@@ -221,6 +228,12 @@ class Scene:
         """bvh_build (cpu/src/bvh.c:360-388); OR RT_BVH_REFBIN for the reference CPU binary's tree."""
         _check(lib().rt_scene_build_bvh(self._h, heuristic))
         return self
+
+    def build_bvh_gpu(self, heuristic=6, device=0) -> rt_bvh_gpu_stats:
+        """The same tree built on the GPU (csrc/bvh_build_gpu.cu); returns the stage timings."""
+        st = rt_bvh_gpu_stats()
+        _check(lib().rt_scene_build_bvh_gpu(self._h, heuristic, device, C.byref(st)))
+        return st
 
     def view(self) -> rt_scene_desc:
         d = rt_scene_desc()
