@@ -286,37 +286,41 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
     slot_params = []
     for slot in range(rt.RT_FRAME_SLOTS):
         slot_params.append(rt.default_params(**base, frame_slot=slot))
+    def e2e_loop(steps):
+        if gather == "nccl":
+            for _ in range(steps):
+                ctx.render_frame(params)
+                assemble()
+                barrier()
+                if rank == 0:
+                    ctx.download_into(pinned[0].data_ptr())
+        elif world == 1:
+            for k in range(steps):
+                s = k % rt.RT_FRAME_SLOTS
+                if k >= rt.RT_FRAME_SLOTS:
+                    ctx.frame_wait(s)           # frame k-2 is on the host (pinned[s] is consumed here)
+                ctx.render_frame_async(slot_params[s])
+                ctx.download_async(s, pinned[s].data_ptr())
+            for s in range(min(steps, rt.RT_FRAME_SLOTS)):
+                ctx.frame_wait(s)
+        else:
+            for k in range(steps):
+                s = k % rt.RT_FRAME_SLOTS
+                ctx.render_frame_async(slot_params[s])
+                ctx.frame_wait(s)               # this rank's tiles of frame k are stored in rank 0's slot s
+                if rank == 0 and k >= 1:
+                    ctx.frame_wait(1 - s)       # D2H of frame k-1 (ran during this render) is complete: slot 1-s is free again
+                barrier()                       # frame k on rank 0 is complete once every rank has stored its tiles
+                if rank == 0:
+                    ctx.download_async(s, pinned[s].data_ptr())
+            if rank == 0:
+                for s in range(min(steps, rt.RT_FRAME_SLOTS)):
+                    ctx.frame_wait(s)
+
+    e2e_loop(max(args.warmup, 4))   # untimed: second frame slot allocation, lazy IPC peer mapping, first NCCL barriers
     barrier(); torch.cuda.synchronize()
     t_e0 = time.perf_counter()
-    if gather == "nccl":
-        for _ in range(args.steps):
-            ctx.render_frame(params)
-            assemble()
-            barrier()
-            if rank == 0:
-                ctx.download_into(pinned[0].data_ptr())
-    elif world == 1:
-        for k in range(args.steps):
-            s = k % rt.RT_FRAME_SLOTS
-            if k >= rt.RT_FRAME_SLOTS:
-                ctx.frame_wait(s)           # frame k-2 is on the host (pinned[s] is consumed here)
-            ctx.render_frame_async(slot_params[s])
-            ctx.download_async(s, pinned[s].data_ptr())
-        for s in range(min(args.steps, rt.RT_FRAME_SLOTS)):
-            ctx.frame_wait(s)
-    else:
-        for k in range(args.steps):
-            s = k % rt.RT_FRAME_SLOTS
-            ctx.render_frame_async(slot_params[s])
-            ctx.frame_wait(s)               # this rank's tiles of frame k are stored in rank 0's slot s
-            if rank == 0 and k >= 1:
-                ctx.frame_wait(1 - s)       # D2H of frame k-1 (ran during this render) is complete: slot 1-s is free again
-            barrier()                       # frame k on rank 0 is complete once every rank has stored its tiles
-            if rank == 0:
-                ctx.download_async(s, pinned[s].data_ptr())
-        if rank == 0:
-            for s in range(min(args.steps, rt.RT_FRAME_SLOTS)):
-                ctx.frame_wait(s)
+    e2e_loop(args.steps)
     torch.cuda.synchronize(); barrier()
     e2e_ms = (time.perf_counter() - t_e0) * 1e3 / args.steps
     # unpipelined reference point: render, wait, copy, wait — one frame at a time

@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -537,6 +538,10 @@ extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt
 #define CKB(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rt::set_error(std::string("rt_scene_build_bvh_gpu: ") + #call + " failed: " + cudaGetErrorString(e__)); return RT_ERR_CUDA; } } while (0)
     const double t_begin = now_ms();
     CKB(cudaSetDevice(device));
+    CKB(cudaFree(nullptr)); // context creation is not part of the build
+    const bool dbg = std::getenv("RT_BVH_GPU_DEBUG") != nullptr;
+    auto mark = [&](const char* what) { if (dbg) { cudaDeviceSynchronize(); std::fprintf(stderr, "[bvh_gpu] %-28s %9.2f ms\n", what, now_ms() - t_begin); } };
+    mark("context");
     cudaStream_t stream = nullptr; // legacy default stream: every step below is ordered, the host waits where it reads back
 
     DevBuf d_tri, d_info, d_idx, d_tmp, d_posl, d_nodes, d_bins, d_flags, d_chunks, d_active, d_chunk_base, d_chunk_nl, d_chunk_off;
@@ -551,10 +556,13 @@ extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt
     CKB(d_posl.alloc(n * 4));
     CKB(d_bins.alloc(max_active * sizeof(BinSet)));
     CKB(d_flags.alloc(sizeof(Flags)));
+    mark("allocations");
     CKB(cudaMemsetAsync(d_flags.p, 0, sizeof(Flags), stream));
     CKB(cudaMemcpyAsync(d_tri.p, s->tri.data(), n * 36, cudaMemcpyHostToDevice, stream));
+    mark("triangles host->device");
     prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_tri.as<float>(), d_info.as<float4>(), d_idx.as<int>(), (int)n, refbin);
     CKB(cudaGetLastError());
+    mark("prepare kernel");
 
     // top nodes live in a host mirror + device array that grows level by level
     std::vector<BNode> top;
@@ -645,6 +653,7 @@ extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt
         for (int a = 0; a < (int)prev.size(); a++) { classify(child_base + 2 * a); classify(child_base + 2 * a + 1); }
         st.levels++;
     }
+    mark("top levels");
     st.top_ms = (float)(now_ms() - t_top);
     st.top_nodes = (int)top.size();
 
@@ -678,6 +687,7 @@ extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt
     Flags fl;
     CKB(cudaMemcpyAsync(&fl, d_flags.p, sizeof fl, cudaMemcpyDeviceToHost, stream));
     CKB(cudaStreamSynchronize(stream));
+    mark("subtrees");
     st.subtree_ms = (float)(now_ms() - t_sub);
     st.subtrees = n_sub;
 
@@ -740,6 +750,7 @@ extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt
     }
     CKB(cudaGetLastError());
     CKB(cudaStreamSynchronize(stream));
+    mark("assemble");
     st.assemble_ms = (float)(now_ms() - t_asm);
 
     const double t_down = now_ms();
@@ -747,6 +758,7 @@ extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt
     s->tri_idx.resize(n);
     CKB(cudaMemcpy(s->bvh.data(), d_out.p, total * sizeof(rt_bvh_node), cudaMemcpyDeviceToHost));
     CKB(cudaMemcpy(s->tri_idx.data(), d_idx.p, n * 4, cudaMemcpyDeviceToHost));
+    mark("download");
     st.download_ms = (float)(now_ms() - t_down);
     st.total_ms = (float)(now_ms() - t_begin);
     st.nodes = (unsigned)total;

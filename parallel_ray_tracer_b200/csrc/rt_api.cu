@@ -410,7 +410,7 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
     // frame storage on device 0 (+ local frames for PEER_COPY)
     Dev& D0 = c->devs[0];
     CK(c, cudaSetDevice(D0.id));
-    if ((rc = ensure(c, &S.bgra, &S.bgra_px, npx))) return rc;
+    if (!S.ipc_frame && (rc = ensure(c, &S.bgra, &S.bgra_px, npx))) return rc; // an imported frame is the target: no local one
     if (p->aov_mask & RT_AOV_RGB_F32) { if ((rc = ensure(c, &D0.rgb, &D0.aov_px[0], 3 * npx))) return rc; }
     if (p->aov_mask & RT_AOV_TRI_ID) { if ((rc = ensure(c, &D0.tri_id, &D0.aov_px[1], npx))) return rc; }
     if (p->aov_mask & RT_AOV_DEPTH) { if ((rc = ensure(c, &D0.depth, &D0.aov_px[2], npx))) return rc; }
@@ -726,7 +726,7 @@ int rt_packed_tiles(rt_ctx* c, void** dev_ptr, size_t* bytes)
     int rc = ensure(c, &D.packed, &D.packed_px, std::max<size_t>((size_t)D.n_tiles * RT_TILE_PIXELS, 1));
     if (rc) return rc;
     if (D.n_tiles) {
-        pack_tiles_kernel<<<D.n_tiles, RT_TILE_PIXELS, 0, D.stream>>>(S.bgra, D.packed, D.tile_list, D.n_tiles, tiles_x_of(c->width), c->width, c->height);
+        pack_tiles_kernel<<<D.n_tiles, RT_TILE_PIXELS, 0, D.stream>>>(S.ipc_frame ? S.ipc_frame : S.bgra, D.packed, D.tile_list, D.n_tiles, tiles_x_of(c->width), c->width, c->height);
         CK(c, cudaGetLastError());
     }
     CK(c, cudaStreamSynchronize(D.stream));
@@ -741,6 +741,7 @@ int rt_unpack_tiles(rt_ctx* c, const void* dev_gathered, size_t stride_bytes, in
     if (!c->rendered) return fail(c, RT_ERR_STATE, "rt_unpack_tiles: nothing rendered yet");
     Dev& D0 = c->devs[0];
     const int w = c->width, h = c->height;
+    if (!c->slots[c->last_slot].bgra) return fail(c, RT_ERR_STATE, "rt_unpack_tiles: this context renders into an imported frame");
     int rc = setup_local_index(c, w, h, part_count);
     if (rc) return rc;
     CK(c, cudaSetDevice(D0.id));
