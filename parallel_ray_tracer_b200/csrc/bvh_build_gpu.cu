@@ -20,8 +20,8 @@
 //
 // Structure: the top of the tree (nodes of >= kSmall triangles) is built level by level with many CTAs per node
 // (binning with shared-memory bins, one global merge per CTA; scan + scatter partition); every node below that size is
-// finished by ONE thread that runs the reference algorithm as is on its private triangle range, thousands of subtrees
-// at once.  Arithmetic: this file is compiled -fmad=false -prec-div=true (csrc/Makefile), the two flavours of
+// the root of a subtree that ONE WARP finishes in the reference's own depth-first order (bins in shared memory, ballot
+// compaction, the same chain rule), thousands of subtrees at once.  Arithmetic: this file is compiled -fmad=false -prec-div=true (csrc/Makefile), the two flavours of
 // bvh_build.cpp (IEEE source reading / the reference CPU binary's four contracted expressions) are both available.
 //
 // Inputs that trip the reference's degenerate-input guards (bvh_len >= 2N, bvh.c:80-83) or would need pathological
@@ -45,7 +45,7 @@ constexpr int kMaxDepth = 32;     // BVH_MAX_ITER, cpu/include/options.h:64
 constexpr int kLeafThreshold = 2; // BVH_ELEMENT_THRESHOLD, cpu/include/options.h:58
 constexpr int kBins = 32;         // SAH_BIN_SIZE, cpu/include/options.h:61
 constexpr int kNB = kBins + 1;    // threshold bins per axis
-constexpr int kSmallDefault = 64;  // nodes below this size are finished by one thread (RT_BVH_GPU_SMALL overrides, for experiments)
+constexpr int kSmallDefault = 256; // nodes below this size are finished by one warp (RT_BVH_GPU_SMALL overrides, for experiments)
 constexpr int kChunk = 2048;      // triangles per CTA work item of the level-synchronous top
 constexpr int kCta = 256;
 constexpr int kPer = kChunk / kCta;
@@ -187,49 +187,55 @@ __global__ void __launch_bounds__(kCta) bin_kernel(const int2* __restrict__ chun
     }
 }
 
-// heuristic 6 (bvh.c:138-177) from the bins of one node.  bin(b): count and vertex bounds of threshold bin b of `axis`.
+// heuristic 6 (bvh.c:138-177) from the bins of one node, one axis: the first candidate plane i (ascending) whose cost is
+// strictly below `best` wins (bvh.c:169-174).  bin(b): count and vertex bounds of threshold bin b of `axis`.
+template <class BinCnt, class BinBox>
+__device__ __forceinline__ void choose_axis(int axis, const float* pmn, const float* pmx, int refbin, BinCnt bin_cnt, BinBox bin_box,
+                                            float& best, int& splitAxis, float& splitPos)
+{
+    const float size = pmx[axis] - pmn[axis];
+    // suffix unions: R_i = bins i+1 .. 32
+    float suf_mn[kNB][3], suf_mx[kNB][3];
+    int sufc[kNB];
+    float acc_mn[3] = {INFINITY, INFINITY, INFINITY}, acc_mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    int accc = 0;
+    for (int b = kBins; b >= 1; b--) {
+        float bm[3], bx[3];
+        bin_box(axis, b, bm, bx);
+        for (int a = 0; a < 3; a++) { acc_mn[a] = fmn(acc_mn[a], bm[a]); acc_mx[a] = fmx(acc_mx[a], bx[a]); }
+        accc += bin_cnt(axis, b);
+        for (int a = 0; a < 3; a++) { suf_mn[b - 1][a] = acc_mn[a]; suf_mx[b - 1][a] = acc_mx[a]; }
+        sufc[b - 1] = accc;
+    }
+    float pre_mn[3] = {INFINITY, INFINITY, INFINITY}, pre_mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    int prec = 0;
+    for (int i = 0; i < kBins; i++) {
+        float bm[3], bx[3];
+        bin_box(axis, i, bm, bx);
+        for (int a = 0; a < 3; a++) { pre_mn[a] = fmn(pre_mn[a], bm[a]); pre_mx[a] = fmx(pre_mx[a], bx[a]); }
+        prec += bin_cnt(axis, i);
+        float al_mn[3], al_mx[3], ar_mn[3], ar_mx[3]; // candidate boxes start at min = FLT_MAX, max = FLT_MIN (bvh.c:149-150)
+        for (int a = 0; a < 3; a++) {
+            al_mn[a] = fmn(FLT_MAX, pre_mn[a]);
+            al_mx[a] = fmx(FLT_MIN, pre_mx[a]);
+            ar_mn[a] = fmn(FLT_MAX, suf_mn[i][a]);
+            ar_mx[a] = fmx(FLT_MIN, suf_mx[i][a]);
+        }
+        const int cl = prec, cr = sufc[i];
+        float score;
+        if (refbin) score = __fmaf_rn((float)cl, diag2(al_mn, al_mx, 1), (float)cr * diag2(ar_mn, ar_mx, 1));
+        else score = (float)cl * diag2(al_mn, al_mx, 0) + (float)cr * diag2(ar_mn, ar_mx, 0); // bvh.c:169
+        if (score < best) { best = score; splitAxis = axis; splitPos = split_plane(pmn[axis], size, i, refbin); }
+    }
+}
+
 template <class BinCnt, class BinBox>
 __device__ __forceinline__ void choose_h6(const float* pmn, const float* pmx, int refbin, BinCnt bin_cnt, BinBox bin_box, int& splitAxis, float& splitPos)
 {
     splitAxis = 0;
     splitPos = 0;
     float best = FLT_MAX;
-    for (int axis = 0; axis < 3; axis++) {
-        const float size = pmx[axis] - pmn[axis];
-        // suffix unions: R_i = bins i+1 .. 32
-        float suf_mn[kNB][3], suf_mx[kNB][3];
-        int sufc[kNB];
-        float acc_mn[3] = {INFINITY, INFINITY, INFINITY}, acc_mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-        int accc = 0;
-        for (int b = kBins; b >= 1; b--) {
-            float bm[3], bx[3];
-            bin_box(axis, b, bm, bx);
-            for (int a = 0; a < 3; a++) { acc_mn[a] = fmn(acc_mn[a], bm[a]); acc_mx[a] = fmx(acc_mx[a], bx[a]); }
-            accc += bin_cnt(axis, b);
-            for (int a = 0; a < 3; a++) { suf_mn[b - 1][a] = acc_mn[a]; suf_mx[b - 1][a] = acc_mx[a]; }
-            sufc[b - 1] = accc;
-        }
-        float pre_mn[3] = {INFINITY, INFINITY, INFINITY}, pre_mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-        int prec = 0;
-        for (int i = 0; i < kBins; i++) {
-            float bm[3], bx[3];
-            bin_box(axis, i, bm, bx);
-            for (int a = 0; a < 3; a++) { pre_mn[a] = fmn(pre_mn[a], bm[a]); pre_mx[a] = fmx(pre_mx[a], bx[a]); }
-            prec += bin_cnt(axis, i);
-            float al_mn[3], al_mx[3], ar_mn[3], ar_mx[3]; // candidate boxes start at min = FLT_MAX, max = FLT_MIN (bvh.c:149-150)
-            for (int a = 0; a < 3; a++) {
-                al_mn[a] = fmn(FLT_MAX, pre_mn[a]);
-                al_mx[a] = fmx(FLT_MIN, pre_mx[a]);
-                ar_mn[a] = fmn(FLT_MAX, suf_mn[i][a]);
-                ar_mx[a] = fmx(FLT_MIN, suf_mx[i][a]);
-            }
-            const int cl = prec, cr = sufc[i];
-            float score;
-            if (refbin) score = __fmaf_rn((float)cl, diag2(al_mn, al_mx, 1), (float)cr * diag2(ar_mn, ar_mx, 1));
-            else score = (float)cl * diag2(al_mn, al_mx, 0) + (float)cr * diag2(ar_mn, ar_mx, 0); // bvh.c:169
-            if (score < best) { best = score; splitAxis = axis; splitPos = split_plane(pmn[axis], size, i, refbin); }
-        }
-    }
+    for (int axis = 0; axis < 3; axis++) choose_axis(axis, pmn, pmx, refbin, bin_cnt, bin_box, best, splitAxis, splitPos);
 }
 
 __global__ void choose_kernel(int n_active, const int* __restrict__ active_ids, BNode* nodes, const BinSet* __restrict__ bins, int child_base, int refbin)
@@ -394,94 +400,153 @@ __global__ void __launch_bounds__(kCta) copyback_kernel(const int2* __restrict__
     for (int i = threadIdx.x; i < cnt; i += kCta) tri_idx[base + i] = dst[base + i];
 }
 
-// ---- one thread per small subtree: the reference algorithm as is (cf. Builder::split in bvh_build.cpp) ----
+// ---- one WARP per small subtree: the reference algorithm node by node in its own (DFS) order, lanes cooperating ----
+// Per node: lanes stride over the triangles for the binning pass (bins in the warp's slice of shared memory), lanes 0-2
+// evaluate one axis each, the partition is the same compaction + chain-following as in the top levels (ballot instead
+// of a block scan), child boxes by a shuffle reduction.  Nodes are written in the order the reference allocates them.
 struct SubRoot { int bfs; int region; int cap; int final_root; int base; int pad[3]; };
+constexpr int kSubWarps = 8; // warps per CTA
 
-__global__ void __launch_bounds__(32) subtree_kernel(int n_sub, const SubRoot* __restrict__ roots, const BNode* __restrict__ nodes, int* tri_idx,
-                                                     const float4* __restrict__ info, rt_bvh_node* region, int* __restrict__ used, int refbin, Flags* flags)
+__global__ void __launch_bounds__(kSubWarps * 32) subtree_kernel(int n_sub, const SubRoot* __restrict__ roots, const BNode* __restrict__ nodes, int* tri_idx,
+                                                                 int* tmp, int* posL, const float4* __restrict__ info, rt_bvh_node* region,
+                                                                 int* __restrict__ used, int refbin, Flags* flags, int* next_sub)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_sub) return;
-    const BNode& R = nodes[roots[k].bfs];
-    rt_bvh_node* T = region + roots[k].region;
-    const int cap = roots[k].cap;
-    {
-        rt_bvh_node r;
-        for (int a = 0; a < 3; a++) { r.min[a] = R.mn[a]; r.max[a] = R.mx[a]; }
-        r.tr_len = R.len; r.idx = R.first;
-        T[0] = r;
-    }
-    int len = 1;
-    int st_node[kMaxDepth + 2], st_depth[kMaxDepth + 2], sp = 0; // DFS: at most one pending right sibling per level
-    st_node[0] = 0; st_depth[0] = R.depth; sp = 1;
-    int cnt[3][kNB];
-    float bmn[3][kNB][3], bmx[3][kNB][3];
-    while (sp) {
-        sp--;
-        const int node_idx = st_node[sp], depth = st_depth[sp];
-        const rt_bvh_node parent = T[node_idx];
-        if (depth == kMaxDepth || parent.tr_len <= kLeafThreshold) { // bvh.c:84
-            if (!parent.tr_len) T[node_idx].idx = 0;               // bvh.c:85-86
-            continue;
+    __shared__ int s_cnt[kSubWarps][3 * kNB];
+    __shared__ float s_mn[kSubWarps][3 * kNB * 3], s_mx[kSubWarps][3 * kNB * 3];
+    __shared__ float s_split[kSubWarps][3][kBins];
+    __shared__ int s_stack[kSubWarps][2 * (kMaxDepth + 2)];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    int* cnt = s_cnt[w];
+    float* bmn = s_mn[w];
+    float* bmx = s_mx[w];
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(next_sub, 1);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= n_sub) break;
+        const BNode& R = nodes[roots[k].bfs];
+        rt_bvh_node* T = region + roots[k].region;
+        const int cap = roots[k].cap;
+        if (lane == 0) {
+            rt_bvh_node r;
+            for (int a = 0; a < 3; a++) { r.min[a] = R.mn[a]; r.max[a] = R.mx[a]; }
+            r.tr_len = R.len; r.idx = R.first;
+            T[0] = r;
+            s_stack[w][0] = 0; s_stack[w][1] = R.depth;
         }
-        if (len + 2 > cap) { flags->region_overflow = 1; break; }
-        const int child_idx = len; // bvh.c:98-99
-        len += 2;
-        // one binning pass over the node's triangles for all three axes
-        float split[3][kBins];
-        for (int axis = 0; axis < 3; axis++) {
-            const float size = parent.max[axis] - parent.min[axis];
-            for (int i = 0; i < kBins; i++) split[axis][i] = split_plane(parent.min[axis], size, i, refbin);
-            for (int b = 0; b < kNB; b++) { cnt[axis][b] = 0; for (int a = 0; a < 3; a++) { bmn[axis][b][a] = INFINITY; bmx[axis][b][a] = -INFINITY; } }
-        }
-        for (int j = parent.idx; j < parent.idx + parent.tr_len; j++) {
-            const int ti = tri_idx[j];
-            const float4 a = info[3 * (size_t)ti], b = info[3 * (size_t)ti + 1], c = info[3 * (size_t)ti + 2];
-            const float cen[3] = {a.x, a.y, a.z};
-            for (int axis = 0; axis < 3; axis++) {
-                const int kb = threshold_bin(split[axis], cen[axis]);
-                cnt[axis][kb]++;
-                float* m = bmn[axis][kb]; float* x = bmx[axis][kb];
-                m[0] = fmn(m[0], a.w); m[1] = fmn(m[1], b.x); m[2] = fmn(m[2], b.y);
-                x[0] = fmx(x[0], b.z); x[1] = fmx(x[1], b.w); x[2] = fmx(x[2], c.x);
+        __syncwarp();
+        int len = 1, sp = 1; // warp-uniform
+        bool overflow = false;
+        while (sp) {
+            sp--;
+            const int node_idx = s_stack[w][2 * sp], depth = s_stack[w][2 * sp + 1];
+            const rt_bvh_node parent = T[node_idx];
+            __syncwarp();
+            if (depth == kMaxDepth || parent.tr_len <= kLeafThreshold) { // bvh.c:84
+                if (!parent.tr_len && lane == 0) T[node_idx].idx = 0;     // bvh.c:85-86
+                continue;
             }
-        }
-        int splitAxis;
-        float splitPos;
-        choose_h6(parent.min, parent.max, refbin, [&](int ax, int b) { return cnt[ax][b]; },
-                  [&](int ax, int b, float* m, float* x) { for (int a = 0; a < 3; a++) { m[a] = bmn[ax][b][a]; x[a] = bmx[ax][b][a]; } },
-                  splitAxis, splitPos);
-        // the reference's forward partition (bvh.c:244-259), literally
-        rt_bvh_node left, right;
-        left.tr_len = 0; left.idx = parent.idx; right.tr_len = 0; right.idx = parent.idx;
-        float lb[6] = {1e10f, 1e10f, 1e10f, -1e10f, -1e10f, -1e10f}, rb[6] = {1e10f, 1e10f, 1e10f, -1e10f, -1e10f, -1e10f}; // bvh.c:104-108
-        for (int i = parent.idx; i < parent.idx + parent.tr_len; i++) {
-            const int t_idx = tri_idx[i];
-            const float4 a = info[3 * (size_t)t_idx], b = info[3 * (size_t)t_idx + 1], c = info[3 * (size_t)t_idx + 2];
-            const float cen = splitAxis == 0 ? a.x : (splitAxis == 1 ? a.y : a.z);
-            const bool inA = cen < splitPos;
-            float* g = inA ? lb : rb;
-            g[0] = fmn(g[0], a.w); g[1] = fmn(g[1], b.x); g[2] = fmn(g[2], b.y);
-            g[3] = fmx(g[3], b.z); g[4] = fmx(g[4], b.w); g[5] = fmx(g[5], c.x);
-            if (inA) {
-                left.tr_len += 1;
-                const int swap = left.idx + left.tr_len - 1;
-                tri_idx[i] = tri_idx[swap];
-                tri_idx[swap] = t_idx;
-                right.idx += 1;
-            } else {
-                right.tr_len += 1;
+            if (len + 2 > cap) { overflow = true; break; }
+            const int child_idx = len; // bvh.c:98-99
+            len += 2;
+            const int first = parent.idx, n_el = parent.tr_len;
+            // ---- binning pass, all three axes ----
+            for (int t = lane; t < 3 * kBins; t += 32) {
+                const int axis = t / kBins, i = t % kBins;
+                s_split[w][axis][i] = split_plane(parent.min[axis], parent.max[axis] - parent.min[axis], i, refbin);
             }
+            for (int b = lane; b < 3 * kNB; b += 32) {
+                cnt[b] = 0;
+                for (int a = 0; a < 3; a++) { bmn[3 * b + a] = INFINITY; bmx[3 * b + a] = -INFINITY; }
+            }
+            __syncwarp();
+            for (int i = lane; i < n_el; i += 32) {
+                const int ti = tri_idx[first + i];
+                const float4 a = info[3 * (size_t)ti], b = info[3 * (size_t)ti + 1], c = info[3 * (size_t)ti + 2];
+                const float cen[3] = {a.x, a.y, a.z}, mn[3] = {a.w, b.x, b.y}, mx[3] = {b.z, b.w, c.x};
+                for (int axis = 0; axis < 3; axis++) {
+                    const int kb = axis * kNB + threshold_bin(s_split[w][axis], cen[axis]);
+                    atomicAdd(&cnt[kb], 1);
+                    for (int d = 0; d < 3; d++) { atomic_min_f(&bmn[3 * kb + d], mn[d]); atomic_max_f(&bmx[3 * kb + d], mx[d]); }
+                }
+            }
+            __syncwarp();
+            // ---- candidates: lane a evaluates axis a; the first strictly smaller cost in axis-major order wins ----
+            float best = FLT_MAX, my_pos = 0.f;
+            int my_axis = 0;
+            if (lane < 3)
+                choose_axis(lane, parent.min, parent.max, refbin, [&](int ax, int b) { return cnt[ax * kNB + b]; },
+                            [&](int ax, int b, float* m, float* x) { for (int a = 0; a < 3; a++) { m[a] = bmn[3 * (ax * kNB + b) + a]; x[a] = bmx[3 * (ax * kNB + b) + a]; } },
+                            best, my_axis, my_pos);
+            int splitAxis = 0;
+            float splitPos = 0.f, run = FLT_MAX;
+            for (int a = 0; a < 3; a++) {
+                const float ba = __shfl_sync(FULL, best, a), pa = __shfl_sync(FULL, my_pos, a);
+                if (ba < run) { run = ba; splitAxis = a; splitPos = pa; }
+            }
+            // ---- partition (bvh.c:244-259): lefts compacted in encounter order, rights by their chains ----
+            float lb[6] = {1e10f, 1e10f, 1e10f, -1e10f, -1e10f, -1e10f}, rb[6] = {1e10f, 1e10f, 1e10f, -1e10f, -1e10f, -1e10f}; // bvh.c:104-108
+            int nl = 0;
+            for (int base = 0; base < n_el; base += 32) {
+                const int i = base + lane;
+                bool inA = false;
+                int ti = 0;
+                if (i < n_el) {
+                    ti = tri_idx[first + i];
+                    const float4 a = info[3 * (size_t)ti], b = info[3 * (size_t)ti + 1], c = info[3 * (size_t)ti + 2];
+                    const float cen = splitAxis == 0 ? a.x : (splitAxis == 1 ? a.y : a.z);
+                    inA = cen < splitPos;
+                    float* g = inA ? lb : rb;
+                    g[0] = fmn(g[0], a.w); g[1] = fmn(g[1], b.x); g[2] = fmn(g[2], b.y);
+                    g[3] = fmx(g[3], b.z); g[4] = fmx(g[4], b.w); g[5] = fmx(g[5], c.x);
+                }
+                const unsigned m = __ballot_sync(FULL, inA);
+                if (inA) {
+                    const int r = nl + __popc(m & ((1u << lane) - 1u));
+                    tmp[first + r] = ti;
+                    posL[first + r] = i;
+                }
+                nl += __popc(m);
+            }
+            __syncwarp();
+            for (int i = lane; i < n_el; i += 32) {
+                const int ti = tri_idx[first + i];
+                const float4 a = info[3 * (size_t)ti];
+                const float cen = splitAxis == 0 ? a.x : (splitAxis == 1 ? a.y : a.z);
+                if (cen < splitPos) continue;
+                int p = i; // chains are at most n_el < kMid long
+                while (p < nl) p = posL[first + p];
+                tmp[first + p] = ti;
+            }
+            __syncwarp();
+            for (int i = lane; i < n_el; i += 32) tri_idx[first + i] = tmp[first + i];
+            for (int d = 0; d < 3; d++) {
+                for (int o = 16; o; o >>= 1) {
+                    lb[d] = fmn(lb[d], __shfl_xor_sync(FULL, lb[d], o)); lb[3 + d] = fmx(lb[3 + d], __shfl_xor_sync(FULL, lb[3 + d], o));
+                    rb[d] = fmn(rb[d], __shfl_xor_sync(FULL, rb[d], o)); rb[3 + d] = fmx(rb[3 + d], __shfl_xor_sync(FULL, rb[3 + d], o));
+                }
+            }
+            if (lane == 0) {
+                rt_bvh_node left, right;
+                left.tr_len = nl; left.idx = first; right.tr_len = n_el - nl; right.idx = first + nl;
+                for (int a = 0; a < 3; a++) { left.min[a] = lb[a]; left.max[a] = lb[3 + a]; right.min[a] = rb[a]; right.max[a] = rb[3 + a]; }
+                T[child_idx] = left;
+                T[child_idx + 1] = right;
+                T[node_idx].idx = child_idx; // bvh.c:262-263
+                T[node_idx].tr_len = 0;
+                s_stack[w][2 * sp] = child_idx + 1; s_stack[w][2 * sp + 1] = depth + 1; // right is popped after the whole left subtree
+                s_stack[w][2 * sp + 2] = child_idx; s_stack[w][2 * sp + 3] = depth + 1;
+            }
+            sp += 2;
+            __syncwarp();
         }
-        for (int a = 0; a < 3; a++) { left.min[a] = lb[a]; left.max[a] = lb[3 + a]; right.min[a] = rb[a]; right.max[a] = rb[3 + a]; }
-        T[child_idx] = left;
-        T[child_idx + 1] = right;
-        T[node_idx].idx = child_idx; // bvh.c:262-263
-        T[node_idx].tr_len = 0;
-        st_node[sp] = child_idx + 1; st_depth[sp] = depth + 1; sp++; // right is popped after the whole left subtree
-        st_node[sp] = child_idx; st_depth[sp] = depth + 1; sp++;
+        if (lane == 0) {
+            used[k] = len;
+            if (overflow) flags->region_overflow = 1;
+        }
+        __syncwarp();
     }
-    used[k] = len;
 }
 
 // ---- numbering: subtrees and top nodes into the reference's node order ----
@@ -660,6 +725,8 @@ extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt
     // ---- small subtrees: one thread each ----
     const double t_sub = now_ms();
     const int n_sub = (int)small_roots.size();
+    // largest first: the warps draw subtrees from a counter, so the long ones should not start last
+    std::stable_sort(small_roots.begin(), small_roots.end(), [&](int a, int b) { return top[(size_t)a].len > top[(size_t)b].len; });
     std::vector<SubRoot> roots((size_t)n_sub);
     size_t region_total = 0;
     for (int k = 0; k < n_sub; k++) {
@@ -679,8 +746,15 @@ extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt
         CKB(d_region.alloc(region_total * sizeof(rt_bvh_node)));
         CKB(d_used.alloc((size_t)n_sub * 4));
         CKB(cudaMemcpyAsync(d_roots.p, roots.data(), (size_t)n_sub * sizeof(SubRoot), cudaMemcpyHostToDevice, stream));
-        subtree_kernel<<<(n_sub + 31) / 32, 32, 0, stream>>>(n_sub, d_roots.as<SubRoot>(), d_nodes.as<BNode>(), d_idx.as<int>(), d_info.as<float4>(),
-                                                             d_region.as<rt_bvh_node>(), d_used.as<int>(), refbin, d_flags.as<Flags>());
+        DevBuf d_next;
+        CKB(d_next.alloc(4));
+        CKB(cudaMemsetAsync(d_next.p, 0, 4, stream));
+        const int sub_ctas = std::min((n_sub + kSubWarps - 1) / kSubWarps, 148 * 8);
+        subtree_kernel<<<sub_ctas, kSubWarps * 32, 0, stream>>>(n_sub, d_roots.as<SubRoot>(), d_nodes.as<BNode>(), d_idx.as<int>(), d_tmp.as<int>(), d_posl.as<int>(),
+                                                              d_info.as<float4>(), d_region.as<rt_bvh_node>(), d_used.as<int>(), refbin, d_flags.as<Flags>(),
+                                                              d_next.as<int>());
+        CKB(cudaGetLastError());
+        CKB(cudaStreamSynchronize(stream)); // d_next is released at the end of this scope
         CKB(cudaGetLastError());
         CKB(cudaMemcpyAsync(used.data(), d_used.p, (size_t)n_sub * 4, cudaMemcpyDeviceToHost, stream));
     }
