@@ -6,7 +6,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <atomic>
+#include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "flatten.h"
@@ -22,6 +25,23 @@ static inline void cross3(const float* a, const float* b, float* o) // vec_cross
     o[2] = a[0] * b[1] - a[1] * b[0];
 }
 
+// The per-triangle and per-node passes are independent per element: chunk them over the host threads
+// (RT_FLATTEN_THREADS overrides the count; small scenes stay on the calling thread).
+template <class F>
+static void parallel_for(size_t count, F f)
+{
+    static const int hw = [] {
+        const char* e = std::getenv("RT_FLATTEN_THREADS");
+        int t = e ? std::atoi(e) : (int)std::thread::hardware_concurrency();
+        return t > 0 ? t : 1;
+    }();
+    const int t = (int)std::min<size_t>((size_t)hw, count / (1u << 15));
+    if (t <= 1) { f((size_t)0, count); return; }
+    std::vector<std::thread> th;
+    for (int i = 0; i < t; i++) th.emplace_back([=] { f(count * i / t, count * (i + 1) / t); });
+    for (auto& x : th) x.join();
+}
+
 int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
 {
     if (!d.n_tris || !d.tri_coords) { err = "scene has no triangles"; return RT_ERR_INVALID; }
@@ -30,13 +50,18 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
     const uint32_t n = d.n_tris, nb = d.bvh_len;
     const uint32_t n_mats = d.n_mats ? d.n_mats : 1;
 
-    for (uint32_t j = 0; j < n; j++)
-        if (d.tri_idx[j] < 0 || (uint32_t)d.tri_idx[j] >= n) { err = "tri_idx entry out of range"; return RT_ERR_INVALID; }
+    std::atomic<int> bad{0};
+    parallel_for(n, [&](size_t lo, size_t hi) {
+        for (size_t j = lo; j < hi; j++)
+            if (d.tri_idx[j] < 0 || (uint32_t)d.tri_idx[j] >= n) bad.store(1);
+    });
+    if (bad.load()) { err = "tri_idx entry out of range"; return RT_ERR_INVALID; }
 
     // ---- triangles in leaf order ----
-    out.tris.assign(16 * (size_t)n, 0.0f);
+    out.tris.resize(16 * (size_t)n);
     out.shade.resize(4 * (size_t)n);
-    for (uint32_t j = 0; j < n; j++) {
+    parallel_for(n, [&](size_t lo, size_t hi) {
+    for (size_t j = lo; j < hi; j++) {
         const uint32_t orig = (uint32_t)d.tri_idx[j];
         const float* c = d.tri_coords + 9 * (size_t)orig;
         float e1[3], e2[3], nn[3];
@@ -48,8 +73,12 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
         q[4] = e1[1]; q[5] = e1[2]; q[6] = e2[0]; q[7] = e2[1];
         q[8] = e2[2]; q[9] = nn[0]; q[10] = nn[1]; q[11] = nn[2];
         std::memcpy(&q[12], &orig, 4);
+        q[13] = q[14] = q[15] = 0.0f;
     }
-    for (uint32_t i = 0; i < n; i++) {
+    });
+    const uint32_t* tri_mat = d.tri_mat;
+    parallel_for(n, [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; i++) {
         const float* c = d.tri_coords + 9 * (size_t)i;
         float e1[3], e2[3], nn[3];
         sub3(c + 3, c, e1);
@@ -58,10 +87,12 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
         const float mag = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]); // vec_mag
         float* s = &out.shade[4 * (size_t)i];
         s[0] = nn[0] / mag; s[1] = nn[1] / mag; s[2] = nn[2] / mag;          // vec_normalize
-        uint32_t m = d.tri_mat ? d.tri_mat[i] : 0;
-        if (m >= n_mats) { err = "material index out of range"; return RT_ERR_INVALID; }
+        uint32_t m = tri_mat ? tri_mat[i] : 0;
+        if (m >= n_mats) { bad.store(1); m = 0; }
         std::memcpy(&s[3], &m, 4);
     }
+    });
+    if (bad.load()) { err = "material index out of range"; return RT_ERR_INVALID; }
 
     // ---- materials / lights ----
     out.mats.assign(12 * (size_t)n_mats, 0.0f);
@@ -86,14 +117,18 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
 
     // ---- nodes: one record per inner node, DFS pre-order ----
     auto is_inner = [&](const rt_bvh_node& b) { return b.tr_len == 0 && b.idx != 0; };
+    {   // leaves of >= 15 triangles (depth-capped) keep their count in a side table: allocate it before the parallel passes
+        std::atomic<int> big{0};
+        parallel_for(nb, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; i++) if (d.bvh[i].tr_len >= RT_LEAF_CNT_ESC_HOST) { big.store(1); break; }
+        });
+        if (big.load()) out.leaf_cnt.assign(n, 0);
+    }
     auto leaf_ref = [&](const rt_bvh_node& b, int32_t& ref) -> bool {
         if (b.tr_len <= 0) { ref = RT_REF_NONE_HOST; return true; } // empty leaf: never pushed
         if (b.idx < 0 || (uint64_t)b.idx + (uint64_t)b.tr_len > n) return false;
         const int cnt = b.tr_len >= RT_LEAF_CNT_ESC_HOST ? RT_LEAF_CNT_ESC_HOST : b.tr_len;
-        if (b.tr_len >= RT_LEAF_CNT_ESC_HOST) {
-            if (out.leaf_cnt.empty()) out.leaf_cnt.assign(n, 0);
-            out.leaf_cnt[b.idx] = b.tr_len;
-        }
+        if (b.tr_len >= RT_LEAF_CNT_ESC_HOST) out.leaf_cnt[b.idx] = b.tr_len; // (a leaf is the child of one node only)
         ref = ~((b.idx << 4) | cnt);
         return true;
     };
@@ -126,7 +161,8 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
     out.max_depth = max_depth;
 
     const size_t n_inner = order.empty() ? 1 : order.size();
-    out.nodes.assign(16 * n_inner, 0.0f);
+    out.nodes.resize(16 * n_inner);
+    if (order.empty()) std::fill(out.nodes.begin(), out.nodes.end(), 0.0f);
     auto put_child = [&](float* q, int which, const rt_bvh_node& c, int32_t ref) {
         float mn[3], mx[3];
         // An empty child must never be entered.  The slab test cannot see an inverted box (it takes min/max of
@@ -148,17 +184,21 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
         put_child(out.nodes.data(), 0, all, ref);
         put_child(out.nodes.data(), 1, d.bvh[0], RT_REF_NONE_HOST);
     }
-    for (size_t k = 0; k < order.size(); k++) {
-        const rt_bvh_node& b = d.bvh[order[k]];
-        float* q = &out.nodes[16 * k];
-        for (int w = 0; w < 2; w++) {
-            const rt_bvh_node& c = d.bvh[b.idx + w];
-            int32_t ref;
-            if (is_inner(c)) ref = inner_of[b.idx + w];
-            else if (!leaf_ref(c, ref)) { err = "BVH leaf range out of bounds"; return RT_ERR_INVALID; }
-            put_child(q, w, c, ref);
+    parallel_for(order.size(), [&](size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; k++) {
+            const rt_bvh_node& b = d.bvh[order[k]];
+            float* q = &out.nodes[16 * k];
+            q[14] = q[15] = 0.0f;
+            for (int w = 0; w < 2; w++) {
+                const rt_bvh_node& c = d.bvh[b.idx + w];
+                int32_t ref = RT_REF_NONE_HOST;
+                if (is_inner(c)) ref = inner_of[b.idx + w];
+                else if (!leaf_ref(c, ref)) { bad.store(1); ref = RT_REF_NONE_HOST; }
+                put_child(q, w, c, ref);
+            }
         }
-    }
+    });
+    if (bad.load()) { err = "BVH leaf range out of bounds"; return RT_ERR_INVALID; }
 
     // ---- 4-wide collapse for the fast build: every other level of the reference tree is skipped ----
     // A BVH4 node holds the (up to four) grandchildren of a reference inner node — a child that is a leaf stays
@@ -189,13 +229,16 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
                 if (is_inner(d.bvh[kids[i]])) stack4.push_back(kids[i]);
         }
         const size_t n4 = order4.empty() ? 1 : order4.size();
-        out.nodes4.assign(32 * n4, 0.0f);
-        for (size_t k = 0; k < n4; k++) { // all slots empty by default: box at +inf, ref NONE
-            float* q = &out.nodes4[32 * k];
-            for (int i = 0; i < 24; i++) q[i] = INFINITY;
-            const int32_t none = RT_REF_NONE_HOST;
-            for (int i = 0; i < 4; i++) std::memcpy(&q[24 + i], &none, 4);
-        }
+        out.nodes4.resize(32 * n4);
+        parallel_for(n4, [&](size_t lo, size_t hi) {
+            for (size_t k = lo; k < hi; k++) { // all slots empty by default: box at +inf, ref NONE
+                float* q = &out.nodes4[32 * k];
+                for (int i = 0; i < 24; i++) q[i] = INFINITY;
+                const int32_t none = RT_REF_NONE_HOST;
+                for (int i = 0; i < 4; i++) std::memcpy(&q[24 + i], &none, 4);
+                for (int i = 28; i < 32; i++) q[i] = 0.0f;
+            }
+        });
         auto put4 = [&](float* q, int slot, const rt_bvh_node& c, int32_t ref) {
             if (ref == RT_REF_NONE_HOST) return;
             q[0 + slot] = c.min[0]; q[4 + slot] = c.min[1]; q[8 + slot] = c.min[2];
@@ -209,20 +252,33 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
             for (int a = 0; a < 3; a++) { all.min[a] = -1e30f; all.max[a] = 1e30f; }
             put4(out.nodes4.data(), 0, all, ref);
         }
-        // stack need of a ray: at a node with c live children one is entered and at most c-1 stay pushed
+        // records (independent per node) ...
+        parallel_for(order4.size(), [&](size_t lo, size_t hi) {
+            for (size_t k = lo; k < hi; k++) {
+                uint32_t kids[4];
+                const int c = kids_of(order4[k], kids);
+                float* q = &out.nodes4[32 * k];
+                for (int i = 0; i < c; i++) {
+                    const rt_bvh_node& ch = d.bvh[kids[i]];
+                    int32_t ref = RT_REF_NONE_HOST;
+                    if (is_inner(ch)) ref = idx4[kids[i]];
+                    else if (!leaf_ref(ch, ref)) { bad.store(1); ref = RT_REF_NONE_HOST; }
+                    put4(q, i, ch, ref);
+                }
+            }
+        });
+        if (bad.load()) { err = "BVH leaf range out of bounds"; return RT_ERR_INVALID; }
+        // ... and the stack need of a ray (bottom-up): at a node with c live children one is entered and at most c-1 stay pushed
         std::vector<int32_t> need4(n4, 0);
         for (size_t k = order4.size(); k-- > 0;) { // children have larger indices than their parent (pre-order)
-            uint32_t kids[4];
-            const int c = kids_of(order4[k], kids);
-            float* q = &out.nodes4[32 * k];
+            const float* q = &out.nodes4[32 * k];
             int live = 0, deepest = 0;
-            for (int i = 0; i < c; i++) {
-                const rt_bvh_node& ch = d.bvh[kids[i]];
+            for (int i = 0; i < 4; i++) {
                 int32_t ref;
-                if (is_inner(ch)) { ref = idx4[kids[i]]; deepest = std::max(deepest, need4[(size_t)ref]); }
-                else if (!leaf_ref(ch, ref)) { err = "BVH leaf range out of bounds"; return RT_ERR_INVALID; }
-                if (ref != RT_REF_NONE_HOST) live++;
-                put4(q, i, ch, ref);
+                std::memcpy(&ref, &q[24 + i], 4);
+                if (ref == RT_REF_NONE_HOST) continue;
+                live++;
+                if (ref >= 0) deepest = std::max(deepest, need4[(size_t)ref]);
             }
             need4[k] = std::max(live - 1, 0) + deepest;
         }

@@ -1,7 +1,9 @@
 // flatten.h — host staging buffers of the HBM layout (device_layout.h), produced by flatten.cpp.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "rt_b200.h"
@@ -13,11 +15,23 @@
 
 namespace rt {
 
+// std::allocator whose value-less construct() default-initialises: resize() of the multi-GB staging arrays does not
+// zero-fill them on one thread first (every element is written by the parallel passes of flatten.cpp).
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInitAlloc<U>; };
+    NoInitAlloc() = default;
+    template <class U> NoInitAlloc(const NoInitAlloc<U>&) {}
+    template <class U> void construct(U* p) { ::new (static_cast<void*>(p)) U; }
+    template <class U, class A0, class... A> void construct(U* p, A0&& a0, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A0>(a0), std::forward<A>(a)...); }
+};
+typedef std::vector<float, NoInitAlloc<float>> FloatBuf;
+
 struct FlatScene {
-    std::vector<float>   nodes;    // 16 floats (4 x float4) per inner node
-    std::vector<float>   nodes4;   // 32 floats (8 x float4) per 4-wide node (fast build)
-    std::vector<float>   tris;     // 16 floats (4 x float4) per leaf-order slot
-    std::vector<float>   shade;    // 4 floats per original triangle
+    FloatBuf             nodes;    // 16 floats (4 x float4) per inner node
+    FloatBuf             nodes4;   // 32 floats (8 x float4) per 4-wide node (fast build)
+    FloatBuf             tris;     // 16 floats (4 x float4) per leaf-order slot
+    FloatBuf             shade;    // 4 floats per original triangle
     std::vector<float>   mats;     // 12 floats per material
     std::vector<float>   lights;   // 8 floats per light
     std::vector<int32_t> leaf_cnt; // empty unless some leaf holds >= 15 triangles

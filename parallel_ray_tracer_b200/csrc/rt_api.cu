@@ -332,13 +332,23 @@ int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** 
             c->copy_stream = D.aux;
             for (int s = 0; s < RT_FRAME_SLOTS; s++) CKC(cudaEventCreateWithFlags(&c->slots[s].copy_done, cudaEventDisableTiming));
         }
-        CKC(upload(&D.nodes, flat.nodes.data(), flat.nodes.size() * 4, D.stream));
-        CKC(upload(&D.nodes4, flat.nodes4.data(), flat.nodes4.size() * 4, D.stream));
-        CKC(upload(&D.tris, flat.tris.data(), flat.tris.size() * 4, D.stream));
-        CKC(upload(&D.shade, flat.shade.data(), flat.shade.size() * 4, D.stream));
-        CKC(upload(&D.mats, flat.mats.data(), flat.mats.size() * 4, D.stream));
-        CKC(upload(&D.lights, flat.lights.data(), flat.lights.size() * 4, D.stream));
-        CKC(upload(&D.leaf_cnt, flat.leaf_cnt.data(), flat.leaf_cnt.size() * 4, D.stream));
+        // One host->device upload (device 0), then fan-out device 0 -> device i over NVLink / NVSwitch: the other devices
+        // do not pull the scene through PCIe again (the reference uploads once to its single device, gpu/src/gpu.cu:143-175).
+        auto put = [&](auto** dst, const void* host, auto* const* src0, size_t bytes) -> cudaError_t {
+            if (i == 0) return upload(dst, host, bytes, D.stream);
+            if (!bytes) { *dst = nullptr; return cudaSuccess; }
+            cudaError_t e = cudaMalloc((void**)dst, bytes);
+            if (e != cudaSuccess) return e;
+            return cudaMemcpyPeerAsync(*dst, D.id, *src0, c->devs[0].id, bytes, D.stream);
+        };
+        Dev& Z = c->devs[0];
+        CKC(put(&D.nodes, flat.nodes.data(), &Z.nodes, flat.nodes.size() * 4));
+        CKC(put(&D.nodes4, flat.nodes4.data(), &Z.nodes4, flat.nodes4.size() * 4));
+        CKC(put(&D.tris, flat.tris.data(), &Z.tris, flat.tris.size() * 4));
+        CKC(put(&D.shade, flat.shade.data(), &Z.shade, flat.shade.size() * 4));
+        CKC(put(&D.mats, flat.mats.data(), &Z.mats, flat.mats.size() * 4));
+        CKC(put(&D.lights, flat.lights.data(), &Z.lights, flat.lights.size() * 4));
+        CKC(put(&D.leaf_cnt, flat.leaf_cnt.data(), &Z.leaf_cnt, flat.leaf_cnt.size() * 4));
         CKC(cudaMalloc((void**)&D.ctrl, 8 * RT_CTRL_WORDS * RT_FRAME_SLOTS));
         CKC(cudaMallocHost((void**)&D.ctrl_host, 64 * RT_FRAME_SLOTS));
         CKC(cudaStreamSynchronize(D.stream));
