@@ -263,6 +263,9 @@ int rt_frame_ipc_import_slot(rt_ctx* ctx, int slot, const void* handle64, int wi
 int rt_debug_warp_trace(rt_ctx* ctx, int enable, unsigned long long* out, int max_warps);
 /* Diagnostics: replace the first device's tile order (tile ids, ty * tiles_x + tx) for the current frame shape. */
 int rt_debug_set_tile_order(rt_ctx* ctx, const unsigned* tiles, int n);
+/* Roofline microbenchmark: GB/s of random 64-byte-record gathers (the shape of a node fetch, one record per
+ * lane) from a working set of ws_bytes on `device` — L1-, L2- or HBM-resident depending on the size. */
+int rt_debug_gather_bandwidth(int device, size_t ws_bytes, float* gbs_out);
 /* Raw device pointer of the BGRA frame (device 0 of the context). */
 int rt_frame_device_ptr(rt_ctx* ctx, void** dev_ptr, size_t* bytes);
 

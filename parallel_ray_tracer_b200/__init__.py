@@ -45,7 +45,7 @@ EXPORTS = [
     "rt_part_tile_count", "rt_packed_tiles", "rt_unpack_tiles", "rt_frame_ipc_export", "rt_frame_ipc_import",
     "rt_frame_device_ptr", "rt_write_bmp", "rt_abi_version", "rt_device_count", "rt_debug_warp_trace",
     "rt_render_async", "rt_download_async", "rt_frame_wait", "rt_host_alloc", "rt_host_free",
-    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order", "rt_scene_build_bvh_gpu",
+    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order", "rt_scene_build_bvh_gpu", "rt_debug_gather_bandwidth",
 ]
 
 
@@ -139,6 +139,7 @@ def lib() -> C.CDLL:
     L.rt_write_bmp.argtypes = [C.c_char_p, vp, i32, i32]
     L.rt_debug_warp_trace.argtypes = [vp, i32, vp, i32]
     L.rt_debug_set_tile_order.argtypes = [vp, vp, i32]
+    L.rt_debug_gather_bandwidth.argtypes = [i32, C.c_size_t, C.POINTER(C.c_float)]
     L.rt_render_async.argtypes = [vp, C.POINTER(rt_render_params)]
     L.rt_download_async.argtypes = [vp, i32, vp]
     L.rt_frame_wait.argtypes = [vp, i32, C.POINTER(rt_timing)]
@@ -422,6 +423,13 @@ class PinnedBuffer:
             self.close()
         except Exception:
             pass
+
+
+def gather_bandwidth(ws_bytes: int, device: int = 0) -> float:
+    """GB/s of random 64-byte-record gathers from a working set of ws_bytes (rt_debug_gather_bandwidth)."""
+    g = C.c_float()
+    _check(lib().rt_debug_gather_bandwidth(device, ws_bytes, C.byref(g)))
+    return g.value
 
 
 def part_tile_count(width, height, part_index, part_count) -> int:

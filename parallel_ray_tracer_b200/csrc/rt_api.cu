@@ -167,6 +167,31 @@ __global__ void unpack_tiles_kernel(uchar4* __restrict__ frame, const uchar4* __
     frame[(size_t)y * width + x] = gathered[(size_t)owner * stride_px + (size_t)li * RT_TILE_PIXELS + p];
 }
 
+// Microbenchmark for the roofline: every lane gathers its own random 64-byte record (two 256-bit loads, the
+// shape of an inner-node fetch) from a working set of `n_rec` records; four independent gathers in flight per lane.
+__global__ void gather64_kernel(const float4* __restrict__ data, unsigned n_rec_mask, int iters, unsigned seed, float4* sink)
+{
+    unsigned x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + seed;
+    float acc = 0.f;
+    for (int i = 0; i < iters; i += 4) {
+        float v[4][16];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            x ^= x << 13; x ^= x >> 17; x ^= x << 5; // xorshift32
+            const float4* p = data + 4 * (size_t)(x & n_rec_mask);
+            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(v[u][0]), "=f"(v[u][1]), "=f"(v[u][2]), "=f"(v[u][3]), "=f"(v[u][4]), "=f"(v[u][5]), "=f"(v[u][6]), "=f"(v[u][7]) : "l"(p));
+            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(v[u][8]), "=f"(v[u][9]), "=f"(v[u][10]), "=f"(v[u][11]), "=f"(v[u][12]), "=f"(v[u][13]), "=f"(v[u][14]), "=f"(v[u][15]) : "l"(p + 2));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int k = 0; k < 16; k++) acc += v[u][k];
+    }
+    if (acc == 123.456f) sink[0] = make_float4(acc, 0, 0, 0);
+}
+
 // ------------------------------------------------------------------ tiles
 inline int tiles_x_of(int w) { return (w + RT_TILE_W - 1) / RT_TILE_W; }
 inline int tiles_y_of(int h) { return (h + RT_TILE_H - 1) / RT_TILE_H; }
@@ -789,6 +814,46 @@ int rt_debug_set_tile_order(rt_ctx* c, const unsigned* tiles, int n)
     if (n != D.n_tiles) return fail(c, RT_ERR_INVALID, "rt_debug_set_tile_order: tile count differs from the current tile list");
     CK(c, cudaSetDevice(D.id));
     CK(c, cudaMemcpy(D.tile_list, tiles, (size_t)n * 4, cudaMemcpyHostToDevice));
+    return RT_OK;
+}
+
+// Random 64-byte-record gather bandwidth of one device for a working set of ws_bytes (rounded down to a power of two):
+// GB/s of records delivered to the lanes.  ws <= L1 size measures L1, a few MB L2 (the shipped scenes), GBs HBM.
+int rt_debug_gather_bandwidth(int device, size_t ws_bytes, float* gbs_out)
+{
+    if (!gbs_out || ws_bytes < 4096) return fail(nullptr, RT_ERR_INVALID, "rt_debug_gather_bandwidth: bad argument");
+    if (rt_device_count() <= device || device < 0) return fail(nullptr, RT_ERR_NO_DEVICE, "rt_debug_gather_bandwidth: no such device");
+    size_t n_rec = 1;
+    while (n_rec * 2 * 64 <= ws_bytes) n_rec *= 2;
+    if (n_rec > (1ull << 31)) n_rec = 1ull << 31;
+    rt_ctx* c = nullptr; // (CK needs a context pointer only for the error text)
+    rt_ctx dummy;
+    c = &dummy;
+    CK(c, cudaSetDevice(device));
+    float4* data = nullptr;
+    float4* sink = nullptr;
+    CK(c, cudaMalloc((void**)&data, n_rec * 64));
+    CK(c, cudaMalloc((void**)&sink, 64));
+    CK(c, cudaMemset(data, 0, n_rec * 64));
+    cudaDeviceProp prop;
+    CK(c, cudaGetDeviceProperties(&prop, device));
+    const int grid = prop.multiProcessorCount * 8, block = 256, iters = 2048;
+    cudaEvent_t e0, e1;
+    CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1));
+    float best = 0.f;
+    for (int rep = 0; rep < 4; rep++) { // rep 0 warms the caches / clocks
+        CK(c, cudaEventRecord(e0));
+        gather64_kernel<<<grid, block>>>(data, (unsigned)(n_rec - 1), iters, 12345u + rep, sink);
+        CK(c, cudaEventRecord(e1));
+        CK(c, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(c, cudaEventElapsedTime(&ms, e0, e1));
+        const float gbs = (float)((double)grid * block * iters * 64.0 / (ms * 1e-3) / 1e9);
+        if (rep > 0 && gbs > best) best = gbs;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(data); cudaFree(sink);
+    *gbs_out = best;
     return RT_OK;
 }
 
