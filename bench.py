@@ -359,6 +359,12 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
     tmw = ctx.render_frame(pw)
     inner = int(allsum(tmw.inner_visits)); tris = int(allsum(tmw.tri_tests))
 
+    # ---- measured gather rooflines of this device (SURVEY §8d: node/triangle bytes over L1/L2/HBM bandwidth) ----
+    gather_peaks = None
+    if rank == 0:
+        gather_peaks = {"l1_resident_64KB": rt.gather_bandwidth(64 << 10, local), "l2_resident_4MB": rt.gather_bandwidth(4 << 20, local),
+                        "hbm_8GB": rt.gather_bandwidth(8 << 30, local)}
+
     # ---- the multi-GPU configuration of BASELINE.json (configs[2]) measured the same way, fewer frames ----
     also = None
     if args.also and args.also != wl_name:
@@ -391,15 +397,16 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
                 ms2.append(tm2.kernel_ms[0])
             torch.cuda.synchronize(); barrier()
             tot2 = allmax(sum(ms2)); rays2 = int(allsum(tm2.rays_closest + tm2.rays_shadow))
+            tmw2 = ctx2.render_frame(rt.default_params(width=W2, height=H2, spp=wl2["spp"], part_index=rank, part_count=world,
+                                                       aov_mask=rt.RT_AOV_WORK, mode=rt.RT_MODE_STRICT))
+            inner2 = int(allsum(tmw2.inner_visits)); tris2 = int(allsum(tmw2.tri_tests))
             also = {"workload": args.also, **wl2, "steps": k2, "ms_per_step": tot2 / k2, "value": rays2 / (tot2 / k2) / 1e3, "unit": METRIC,
                     "rays_per_frame": rays2, "note": "same timing rules as value (CUDA events, max over ranks, L2 flushed), fused peer stores"}
+            if rank == 0:
+                ach2 = (64 * inner2 + 40 * tris2) / world / (tot2 / k2 * 1e-3) / 1e9
+                also["roofline_gather"] = {"unit": "GB/s", "achieved_algorithmic": ach2, "frac_of_l1": ach2 / gather_peaks["l1_resident_64KB"],
+                                           "frac_of_l2": ach2 / gather_peaks["l2_resident_4MB"], "frac_of_hbm_stream_peak": ach2 / peaks()["hbm_gbs"]}
         ctx2.close()
-
-    # ---- measured gather rooflines of this device (SURVEY §8d: node/triangle bytes over L1/L2/HBM bandwidth) ----
-    gather_peaks = None
-    if rank == 0:
-        gather_peaks = {"l1_resident_64KB": rt.gather_bandwidth(64 << 10, local), "l2_resident_4MB": rt.gather_bandwidth(4 << 20, local),
-                        "hbm_8GB": rt.gather_bandwidth(8 << 30, local)}
 
     out = None
     if rank == 0:
