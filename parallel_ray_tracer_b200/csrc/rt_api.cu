@@ -837,11 +837,11 @@ int rt_debug_gather_bandwidth(int device, size_t ws_bytes, float* gbs_out)
     CK(c, cudaMemset(data, 0, n_rec * 64));
     cudaDeviceProp prop;
     CK(c, cudaGetDeviceProperties(&prop, device));
-    const int grid = prop.multiProcessorCount * 8, block = 256, iters = 2048;
+    const int grid = prop.multiProcessorCount * 8, block = 256, iters = 512;
     cudaEvent_t e0, e1;
     CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1));
     float best = 0.f;
-    for (int rep = 0; rep < 4; rep++) { // rep 0 warms the caches / clocks
+    for (int rep = 0; rep < 3; rep++) { // rep 0 warms the caches / clocks
         CK(c, cudaEventRecord(e0));
         gather64_kernel<<<grid, block>>>(data, (unsigned)(n_rec - 1), iters, 12345u + rep, sink);
         CK(c, cudaEventRecord(e1));
