@@ -59,6 +59,41 @@ def test_no_cpu_fallback(rt, scene_arrays):
     assert e.value.code == rt.RT_ERR_NO_DEVICE
 
 
+def test_gpu_only_entry_points_fail_loudly_without_a_device(rt):
+    """The GPU BVH build, pinned allocation and the roofline microbenchmark have no host stand-in either."""
+    if rt.device_count() > 0:
+        pytest.skip("a GPU is present")
+    sc = rt.Scene.load_rtsc(ROOT / "tests" / "golden" / "scenes" / "soup2k.rtsc")
+    with pytest.raises(rt.RtError) as e:
+        sc.build_bvh_gpu(6)
+    assert e.value.code == rt.RT_ERR_NO_DEVICE
+    with pytest.raises(rt.RtError) as e:
+        rt.PinnedBuffer(4096)
+    assert e.value.code == rt.RT_ERR_NO_DEVICE
+    with pytest.raises(rt.RtError) as e:
+        rt.gather_bandwidth(1 << 20)
+    assert e.value.code == rt.RT_ERR_NO_DEVICE
+    with pytest.raises(rt.RtError) as e:
+        sc.build_bvh_gpu(1)   # only heuristic 6 is built on the GPU
+    assert e.value.code == rt.RT_ERR_INVALID
+
+
+def test_bmp_writers_agree(rt, tmp_path):
+    """rt_write_bmp (top-down input, flips) and rt_write_bmp_bottom_up (kernel-ordered rows, no flip) give the same file,
+    with the reference's 54-byte header (cpu/src/bmp_writer.c:97-175)."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (37, 53, 4), dtype=np.uint8)
+    rt.write_bmp(tmp_path / "a.bmp", img)
+    rt.write_bmp_bottom_up(tmp_path / "b.bmp", img[::-1])
+    a, b = (tmp_path / "a.bmp").read_bytes(), (tmp_path / "b.bmp").read_bytes()
+    assert a == b and len(a) == 54 + 37 * 53 * 4 and a[:2] == b"BM"
+    assert int.from_bytes(a[2:6], "little") == len(a) and int.from_bytes(a[10:14], "little") == 54
+    assert int.from_bytes(a[18:22], "little") == 53 and int.from_bytes(a[22:26], "little") == 37 and a[28] == 32
+    rows = np.frombuffer(a, np.uint8, 37 * 53 * 4, 54).reshape(37, 53, 4)
+    assert np.array_equal(rows[::-1], img)
+
+
 def test_product_does_not_reference_the_oracle():
     """Nothing under the package (sources or Python) may import, link or execute oracle/."""
     pkg = ROOT / "parallel_ray_tracer_b200"
