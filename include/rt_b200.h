@@ -208,6 +208,11 @@ void rt_render_params_default(rt_render_params* p); /* reference defaults: 1920x
 /* load_to_gpu: flatten + compress the scene and upload it to every listed device.
  * devices == NULL / ndev == 0 means device 0 only.  desc->bvh must be present. */
 int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** out);
+/* The same context without the tree visiting the host: the heuristic-6 BVH (optionally | RT_BVH_REFBIN) is built on
+ * devices[0], flattened there and fanned out to the other devices over NVLink.  download_tree != 0 also fills the host
+ * scene's bvh / tri_idx (as rt_scene_build_bvh_gpu does); otherwise the host scene is left without a tree.  Renders are
+ * identical to rt_scene_build_bvh + rt_create. */
+int rt_create_gpu(rt_scene* s, int heuristic, const int* devices, int ndev, int download_tree, rt_ctx** out, rt_bvh_gpu_stats* stats_out);
 /* render_frame: blocking; renders into device-resident frame(s). */
 int rt_render(rt_ctx* ctx, const rt_render_params* params, rt_timing* timing_out);
 /* load_from_gpu: copy the last rendered frame (of the slot rendered last) to host; blocking.  bgra: W*H*4 bytes, row 0 = top, bytes

@@ -45,7 +45,7 @@ EXPORTS = [
     "rt_part_tile_count", "rt_packed_tiles", "rt_unpack_tiles", "rt_frame_ipc_export", "rt_frame_ipc_import",
     "rt_frame_device_ptr", "rt_write_bmp", "rt_abi_version", "rt_device_count", "rt_debug_warp_trace",
     "rt_render_async", "rt_download_async", "rt_frame_wait", "rt_host_alloc", "rt_host_free",
-    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order", "rt_scene_build_bvh_gpu", "rt_debug_gather_bandwidth",
+    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order", "rt_scene_build_bvh_gpu", "rt_debug_gather_bandwidth", "rt_create_gpu",
 ]
 
 
@@ -126,6 +126,7 @@ def lib() -> C.CDLL:
     L.rt_scene_free.argtypes = [vp]; L.rt_scene_free.restype = None
     L.rt_render_params_default.argtypes = [C.POINTER(rt_render_params)]; L.rt_render_params_default.restype = None
     L.rt_create.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(i32), i32, C.POINTER(vp)]
+    L.rt_create_gpu.argtypes = [vp, i32, C.POINTER(i32), i32, i32, C.POINTER(vp), C.POINTER(rt_bvh_gpu_stats)]
     L.rt_render.argtypes = [vp, C.POINTER(rt_render_params), C.POINTER(rt_timing)]
     L.rt_download.argtypes = [vp, vp, vp, vp, vp]
     L.rt_destroy.argtypes = [vp]; L.rt_destroy.restype = None
@@ -301,6 +302,19 @@ class Context:
         _check(rc)
         self._h = h
         self.last = None
+
+    @classmethod
+    def build_on_gpu(cls, scene: "Scene", devices=None, heuristic=6, download_tree=False):
+        """rt_create_gpu: BVH build + flatten on the device, no host round trip of the tree.  Returns (context, stats)."""
+        h = C.c_void_p()
+        st = rt_bvh_gpu_stats()
+        arr = (C.c_int * len(devices))(*devices) if devices else None
+        _check(lib().rt_create_gpu(scene._h, heuristic, arr, len(devices) if devices else 0, int(download_tree), C.byref(h), C.byref(st)))
+        self = cls.__new__(cls)
+        self._h = h
+        self.last = None
+        self.build_stats = st
+        return self
 
     def render_frame(self, params: rt_render_params = None, **kw) -> rt_timing:
         """render_frame (gpu/src/gpu.cu:98-127): blocking; returns CUDA-event timings + ray counts."""

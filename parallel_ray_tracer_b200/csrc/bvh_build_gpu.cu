@@ -37,6 +37,7 @@
 #include <string>
 #include <vector>
 
+#include "gpu_tree.h"
 #include "host_scene.h"
 
 namespace {
@@ -409,7 +410,7 @@ constexpr int kSubWarps = 8; // warps per CTA
 
 __global__ void __launch_bounds__(kSubWarps * 32) subtree_kernel(int n_sub, const SubRoot* __restrict__ roots, const BNode* __restrict__ nodes, int* tri_idx,
                                                                  int* tmp, int* posL, const float4* __restrict__ info, rt_bvh_node* region,
-                                                                 int* __restrict__ used, int refbin, Flags* flags, int* next_sub)
+                                                                 unsigned char* region_depth, int* __restrict__ used, int refbin, Flags* flags, int* next_sub)
 {
     __shared__ int s_cnt[kSubWarps][3 * kNB];
     __shared__ float s_mn[kSubWarps][3 * kNB * 3], s_mx[kSubWarps][3 * kNB * 3];
@@ -427,8 +428,10 @@ __global__ void __launch_bounds__(kSubWarps * 32) subtree_kernel(int n_sub, cons
         if (k >= n_sub) break;
         const BNode& R = nodes[roots[k].bfs];
         rt_bvh_node* T = region + roots[k].region;
+        unsigned char* Tdepth = region_depth + roots[k].region;
         const int cap = roots[k].cap;
         if (lane == 0) {
+            Tdepth[0] = (unsigned char)R.depth;
             rt_bvh_node r;
             for (int a = 0; a < 3; a++) { r.min[a] = R.mn[a]; r.max[a] = R.mx[a]; }
             r.tr_len = R.len; r.idx = R.first;
@@ -533,6 +536,7 @@ __global__ void __launch_bounds__(kSubWarps * 32) subtree_kernel(int n_sub, cons
                 for (int a = 0; a < 3; a++) { left.min[a] = lb[a]; left.max[a] = lb[3 + a]; right.min[a] = rb[a]; right.max[a] = rb[3 + a]; }
                 T[child_idx] = left;
                 T[child_idx + 1] = right;
+                Tdepth[child_idx] = Tdepth[child_idx + 1] = (unsigned char)(depth + 1);
                 T[node_idx].idx = child_idx; // bvh.c:262-263
                 T[node_idx].tr_len = 0;
                 s_stack[w][2 * sp] = child_idx + 1; s_stack[w][2 * sp + 1] = depth + 1; // right is popped after the whole left subtree
@@ -550,8 +554,9 @@ __global__ void __launch_bounds__(kSubWarps * 32) subtree_kernel(int n_sub, cons
 }
 
 // ---- numbering: subtrees and top nodes into the reference's node order ----
-__global__ void assemble_subtrees_kernel(const SubRoot* __restrict__ roots, const rt_bvh_node* __restrict__ region, const int* __restrict__ used,
-                                         rt_bvh_node* __restrict__ out)
+__global__ void assemble_subtrees_kernel(const SubRoot* __restrict__ roots, const rt_bvh_node* __restrict__ region,
+                                         const unsigned char* __restrict__ region_depth, const int* __restrict__ used,
+                                         rt_bvh_node* __restrict__ out, unsigned char* __restrict__ out_depth)
 {
     const SubRoot r = roots[blockIdx.x];
     const rt_bvh_node* T = region + r.region;
@@ -559,15 +564,17 @@ __global__ void assemble_subtrees_kernel(const SubRoot* __restrict__ roots, cons
     for (int j = threadIdx.x; j < m; j += blockDim.x) {
         rt_bvh_node nd = T[j];
         if (nd.tr_len == 0 && nd.idx != 0) nd.idx = r.base + (nd.idx - 1);
-        out[j == 0 ? r.final_root : r.base + j - 1] = nd;
+        const int f = j == 0 ? r.final_root : r.base + j - 1;
+        out[f] = nd;
+        out_depth[f] = region_depth[r.region + j];
     }
 }
 
-struct TopRec { int f; rt_bvh_node nd; };
-__global__ void scatter_top_kernel(const TopRec* __restrict__ recs, int n, rt_bvh_node* __restrict__ out)
+struct TopRec { int f; int depth; rt_bvh_node nd; };
+__global__ void scatter_top_kernel(const TopRec* __restrict__ recs, int n, rt_bvh_node* __restrict__ out, unsigned char* __restrict__ out_depth)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[recs[i].f] = recs[i].nd;
+    if (i < n) { out[recs[i].f] = recs[i].nd; out_depth[recs[i].f] = (unsigned char)recs[i].depth; }
 }
 
 struct DevBuf {
@@ -586,12 +593,18 @@ double now_ms()
 
 extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt_bvh_gpu_stats* stats)
 {
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    if (!s) { rt::set_error("rt_scene_build_bvh_gpu: null scene"); return RT_ERR_INVALID; }
+    if ((heuristic & ~RT_BVH_REFBIN) != 6) { rt::set_error("rt_scene_build_bvh_gpu: only heuristic 6 is built on the GPU (use rt_scene_build_bvh for 0 / 1)"); return RT_ERR_INVALID; }
+    return rt::gpu_build_bvh(*s, (heuristic & RT_BVH_REFBIN) ? 1 : 0, device, stats, nullptr);
+}
+
+int rt::gpu_build_bvh(rt_scene& scene, int refbin, int device, rt_bvh_gpu_stats* stats, GpuTree* keep)
+{
+    rt_scene* s = &scene;
     rt_bvh_gpu_stats st;
     std::memset(&st, 0, sizeof st);
     if (stats) *stats = st;
-    if (!s) { rt::set_error("rt_scene_build_bvh_gpu: null scene"); return RT_ERR_INVALID; }
-    const int refbin = (heuristic & RT_BVH_REFBIN) ? 1 : 0;
-    if ((heuristic & ~RT_BVH_REFBIN) != 6) { rt::set_error("rt_scene_build_bvh_gpu: only heuristic 6 is built on the GPU (use rt_scene_build_bvh for 0 / 1)"); return RT_ERR_INVALID; }
     const size_t n = s->n_tris();
     if (n == 0) { rt::set_error("no triangles, cannot build bvh"); return RT_ERR_INVALID; } // bvh.c:361-364
     if (n >= (1u << 27)) { rt::set_error("more than 2^27 triangles"); return RT_ERR_INVALID; }
@@ -739,11 +752,12 @@ extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt
         roots[(size_t)k] = r;
     }
     if (region_total >= (size_t)INT32_MAX) { rt::set_error("rt_scene_build_bvh_gpu: subtree regions exceed 2^31 nodes"); return RT_ERR_NOMEM; }
-    DevBuf d_roots, d_region, d_used, d_out, d_recs;
+    DevBuf d_roots, d_region, d_region_depth, d_used, d_out, d_out_depth, d_recs;
     std::vector<int> used((size_t)n_sub, 1);
     if (n_sub) {
         CKB(d_roots.alloc((size_t)n_sub * sizeof(SubRoot)));
         CKB(d_region.alloc(region_total * sizeof(rt_bvh_node)));
+        CKB(d_region_depth.alloc(region_total));
         CKB(d_used.alloc((size_t)n_sub * 4));
         CKB(cudaMemcpyAsync(d_roots.p, roots.data(), (size_t)n_sub * sizeof(SubRoot), cudaMemcpyHostToDevice, stream));
         DevBuf d_next;
@@ -751,8 +765,8 @@ extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt
         CKB(cudaMemsetAsync(d_next.p, 0, 4, stream));
         const int sub_ctas = std::min((n_sub + kSubWarps - 1) / kSubWarps, 148 * 8);
         subtree_kernel<<<sub_ctas, kSubWarps * 32, 0, stream>>>(n_sub, d_roots.as<SubRoot>(), d_nodes.as<BNode>(), d_idx.as<int>(), d_tmp.as<int>(), d_posl.as<int>(),
-                                                              d_info.as<float4>(), d_region.as<rt_bvh_node>(), d_used.as<int>(), refbin, d_flags.as<Flags>(),
-                                                              d_next.as<int>());
+                                                              d_info.as<float4>(), d_region.as<rt_bvh_node>(), d_region_depth.as<unsigned char>(), d_used.as<int>(), refbin,
+                                                              d_flags.as<Flags>(), d_next.as<int>());
         CKB(cudaGetLastError());
         CKB(cudaStreamSynchronize(stream)); // d_next is released at the end of this scope
         CKB(cudaGetLastError());
@@ -775,6 +789,7 @@ extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt
         st.fell_back = 1;
         st.total_ms = (float)(now_ms() - t_begin);
         if (stats) *stats = st;
+        if (keep) keep->fell_back = true;
         return rt::build_bvh(*s, 6, refbin ? rt::BVH_REFBIN : rt::BVH_IEEE, 0);
     }
     std::vector<int> task_of(top.size(), -1);
@@ -798,6 +813,7 @@ extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt
             }
             TopRec r;
             r.f = it.f;
+            r.depth = b.depth;
             for (int a = 0; a < 3; a++) { r.nd.min[a] = b.mn[a]; r.nd.max[a] = b.mx[a]; }
             if (b.child >= 0) {
                 r.nd.tr_len = 0;
@@ -814,13 +830,16 @@ extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt
         total = (size_t)counter;
     }
     CKB(d_out.alloc(total * sizeof(rt_bvh_node)));
+    CKB(d_out_depth.alloc(total));
     CKB(d_recs.alloc(recs.size() * sizeof(TopRec)));
     CKB(cudaMemcpyAsync(d_recs.p, recs.data(), recs.size() * sizeof(TopRec), cudaMemcpyHostToDevice, stream));
     if (!recs.empty())
-        scatter_top_kernel<<<(unsigned)((recs.size() + 255) / 256), 256, 0, stream>>>(d_recs.as<TopRec>(), (int)recs.size(), d_out.as<rt_bvh_node>());
+        scatter_top_kernel<<<(unsigned)((recs.size() + 255) / 256), 256, 0, stream>>>(d_recs.as<TopRec>(), (int)recs.size(), d_out.as<rt_bvh_node>(),
+                                                                                      d_out_depth.as<unsigned char>());
     if (n_sub) {
         CKB(cudaMemcpyAsync(d_roots.p, roots.data(), (size_t)n_sub * sizeof(SubRoot), cudaMemcpyHostToDevice, stream));
-        assemble_subtrees_kernel<<<n_sub, 128, 0, stream>>>(d_roots.as<SubRoot>(), d_region.as<rt_bvh_node>(), d_used.as<int>(), d_out.as<rt_bvh_node>());
+        assemble_subtrees_kernel<<<n_sub, 128, 0, stream>>>(d_roots.as<SubRoot>(), d_region.as<rt_bvh_node>(), d_region_depth.as<unsigned char>(), d_used.as<int>(),
+                                                            d_out.as<rt_bvh_node>(), d_out_depth.as<unsigned char>());
     }
     CKB(cudaGetLastError());
     CKB(cudaStreamSynchronize(stream));
@@ -828,10 +847,20 @@ extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt
     st.assemble_ms = (float)(now_ms() - t_asm);
 
     const double t_down = now_ms();
-    s->bvh.resize(total);
-    s->tri_idx.resize(n);
-    CKB(cudaMemcpy(s->bvh.data(), d_out.p, total * sizeof(rt_bvh_node), cudaMemcpyDeviceToHost));
-    CKB(cudaMemcpy(s->tri_idx.data(), d_idx.p, n * 4, cudaMemcpyDeviceToHost));
+    if (keep) {
+        // the tree stays on the device: hand the four arrays over, nothing visits the host
+        keep->release();
+        keep->device = device; keep->n_tris = n; keep->n_nodes = total; keep->fell_back = false;
+        keep->tri = d_tri.as<float>(); d_tri.p = nullptr;
+        keep->tri_idx = d_idx.as<int>(); d_idx.p = nullptr;
+        keep->nodes = d_out.as<rt_bvh_node>(); d_out.p = nullptr;
+        keep->depth = d_out_depth.as<unsigned char>(); d_out_depth.p = nullptr;
+    } else {
+        s->bvh.resize(total);
+        s->tri_idx.resize(n);
+        CKB(cudaMemcpy(s->bvh.data(), d_out.p, total * sizeof(rt_bvh_node), cudaMemcpyDeviceToHost));
+        CKB(cudaMemcpy(s->tri_idx.data(), d_idx.p, n * 4, cudaMemcpyDeviceToHost));
+    }
     mark("download");
     st.download_ms = (float)(now_ms() - t_down);
     st.total_ms = (float)(now_ms() - t_begin);

@@ -42,6 +42,32 @@ static void parallel_for(size_t count, F f)
     for (auto& x : th) x.join();
 }
 
+// materials and lights (a few hundred bytes): shared by the host flatten and the device-side one (flatten_gpu.cu)
+void flatten_small(const rt_scene_desc& d, FlatScene& out)
+{
+    const uint32_t n_mats = d.n_mats ? d.n_mats : 1;
+    out.mats.assign(12 * (size_t)n_mats, 0.0f);
+    for (uint32_t m = 0; m < d.n_mats; m++) {
+        const float* k = d.materials + 9 * (size_t)m;
+        float* q = &out.mats[12 * (size_t)m];
+        q[0] = k[0]; q[1] = k[1]; q[2] = k[2];
+        q[4] = k[3]; q[5] = k[4]; q[6] = k[5];
+        q[8] = k[6]; q[9] = k[7]; q[10] = k[8];
+        const float kr_mag = std::sqrt(k[6] * k[6] + k[7] * k[7] + k[8] * k[8]);
+        q[11] = (kr_mag > 0.0) ? 1.0f : 0.0f; // vec_mag(&kr) > 0.0, raytracer.c:168
+    }
+    out.lights.assign(8 * (size_t)(d.n_lights ? d.n_lights : 1), 0.0f);
+    for (uint32_t l = 0; l < d.n_lights; l++) {
+        const float* s = d.lights + 6 * (size_t)l;
+        float* q = &out.lights[8 * (size_t)l];
+        q[0] = s[0]; q[1] = s[1]; q[2] = s[2];
+        q[4] = s[3]; q[5] = s[4]; q[6] = s[5];
+    }
+    out.n_lights = d.n_lights;
+    std::memcpy(out.ambient, d.ambient, 12);
+
+}
+
 int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
 {
     if (!d.n_tris || !d.tri_coords) { err = "scene has no triangles"; return RT_ERR_INVALID; }
@@ -94,26 +120,7 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
     });
     if (bad.load()) { err = "material index out of range"; return RT_ERR_INVALID; }
 
-    // ---- materials / lights ----
-    out.mats.assign(12 * (size_t)n_mats, 0.0f);
-    for (uint32_t m = 0; m < d.n_mats; m++) {
-        const float* k = d.materials + 9 * (size_t)m;
-        float* q = &out.mats[12 * (size_t)m];
-        q[0] = k[0]; q[1] = k[1]; q[2] = k[2];
-        q[4] = k[3]; q[5] = k[4]; q[6] = k[5];
-        q[8] = k[6]; q[9] = k[7]; q[10] = k[8];
-        const float kr_mag = std::sqrt(k[6] * k[6] + k[7] * k[7] + k[8] * k[8]);
-        q[11] = (kr_mag > 0.0) ? 1.0f : 0.0f; // vec_mag(&kr) > 0.0, raytracer.c:168
-    }
-    out.lights.assign(8 * (size_t)(d.n_lights ? d.n_lights : 1), 0.0f);
-    for (uint32_t l = 0; l < d.n_lights; l++) {
-        const float* s = d.lights + 6 * (size_t)l;
-        float* q = &out.lights[8 * (size_t)l];
-        q[0] = s[0]; q[1] = s[1]; q[2] = s[2];
-        q[4] = s[3]; q[5] = s[4]; q[6] = s[5];
-    }
-    out.n_lights = d.n_lights;
-    std::memcpy(out.ambient, d.ambient, 12);
+    flatten_small(d, out);
 
     // ---- nodes: one record per inner node, DFS pre-order ----
     auto is_inner = [&](const rt_bvh_node& b) { return b.tr_len == 0 && b.idx != 0; };

@@ -47,5 +47,6 @@ struct FlatScene {
 };
 
 int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err);
+void flatten_small(const rt_scene_desc& d, FlatScene& out); // mats, lights, n_lights, ambient only
 
 } // namespace rt

@@ -1,0 +1,228 @@
+// flatten_gpu.cu — reference-layout tree (GpuTree, on the device) -> the HBM layout of device_layout.h, on the device.
+// The device-side twin of flatten.cpp: same records bit for bit (this file is compiled -fmad=false -prec-div=true
+// -prec-sqrt=true like the host file is compiled -ffp-contract=off), so a scene can go from triangles to a render-ready
+// context without its tree visiting the host (gpu/src/gpu.cu:129-201 marshals on the host and copies synchronously).
+//
+// What makes it parallel: in the reference's node numbering the k-th node that was split — pre-order rank k among the
+// inner nodes, which is the record index flatten.cpp assigns by a depth-first walk — has its children at 1 + 2k, so
+// record index = (child index - 1) / 2 with no traversal.  The 4-wide collapse keeps the inner nodes at even depth
+// (flatten.cpp: kids_of), in the same pre-order: their indices are an exclusive scan of the even-depth flags.  The
+// per-node stack need of the 4-wide tree is a bottom-up maximum, done level by level (<= 17 levels).
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+
+#include <cmath>
+#include <string>
+
+#include "device_layout.h"
+#include "gpu_tree.h"
+
+namespace {
+
+__device__ __forceinline__ bool is_inner(const rt_bvh_node& b) { return b.tr_len == 0 && b.idx != 0; }
+__device__ __forceinline__ int leaf_ref(const rt_bvh_node& b) // flatten.cpp: leaf_ref
+{
+    if (b.tr_len <= 0) return RT_REF_NONE; // empty leaf: never pushed
+    const int cnt = b.tr_len >= RT_LEAF_CNT_ESC ? RT_LEAF_CNT_ESC : b.tr_len;
+    return ~((b.idx << 4) | cnt);
+}
+
+struct FlatFlags { int bad_material, need_leaf_cnt, max_depth, bad_leaf; };
+
+// triangles in leaf order: (v0, e1, e2, n = e1 x e2, original index), raytracer.c:36-38
+__global__ void tris_kernel(int n, const float* __restrict__ tri, const int* __restrict__ tri_idx, float4* __restrict__ out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int orig = tri_idx[j];
+    const float* c = tri + 9 * (size_t)orig;
+    const float e1[3] = {c[3] - c[0], c[4] - c[1], c[5] - c[2]};
+    const float e2[3] = {c[6] - c[0], c[7] - c[1], c[8] - c[2]};
+    const float nn[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]}; // vec_cross
+    float4* q = out + 4 * (size_t)j;
+    q[0] = make_float4(c[0], c[1], c[2], e1[0]);
+    q[1] = make_float4(e1[1], e1[2], e2[0], e2[1]);
+    q[2] = make_float4(e2[2], nn[0], nn[1], nn[2]);
+    q[3] = make_float4(__int_as_float(orig), 0.f, 0.f, 0.f);
+}
+
+// unit normal norm[0] + material index per original triangle, triangle.c:14-17
+__global__ void shade_kernel(int n, const float* __restrict__ tri, const unsigned* __restrict__ tri_mat, unsigned n_mats, float4* __restrict__ out, FlatFlags* flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* c = tri + 9 * (size_t)i;
+    const float e1[3] = {c[3] - c[0], c[4] - c[1], c[5] - c[2]};
+    const float e2[3] = {c[6] - c[0], c[7] - c[1], c[8] - c[2]};
+    const float nn[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+    const float mag = sqrtf(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]); // vec_mag
+    unsigned m = tri_mat ? tri_mat[i] : 0u;
+    if (m >= n_mats) { flags->bad_material = 1; m = 0; }
+    out[i] = make_float4(nn[0] / mag, nn[1] / mag, nn[2] / mag, __uint_as_float(m)); // vec_normalize
+}
+
+__device__ __forceinline__ void child_box(const rt_bvh_node& c, int ref, float* mn, float* mx)
+{
+    // an empty child must never be entered: degenerate box at +infinity (flatten.cpp: put_child)
+    for (int a = 0; a < 3; a++) { mn[a] = ref == RT_REF_NONE ? INFINITY : c.min[a]; mx[a] = ref == RT_REF_NONE ? INFINITY : c.max[a]; }
+}
+
+__device__ __forceinline__ int child_ref(const rt_bvh_node& c, int n_tris, int* leaf_cnt, FlatFlags* flags)
+{
+    if (is_inner(c)) return (c.idx - 1) >> 1;
+    if (c.tr_len > 0 && (c.idx < 0 || (long long)c.idx + c.tr_len > n_tris)) { flags->bad_leaf = 1; return RT_REF_NONE; }
+    if (c.tr_len >= RT_LEAF_CNT_ESC) {
+        if (leaf_cnt) leaf_cnt[c.idx] = c.tr_len;
+        else flags->need_leaf_cnt = 1;
+    }
+    return leaf_ref(c);
+}
+
+// 2-wide records: one per inner node, index = pre-order rank = (child index - 1) / 2; even-depth flags for the 4-wide scan
+__global__ void nodes_kernel(int n_nodes, int n_tris, const rt_bvh_node* __restrict__ nodes, const unsigned char* __restrict__ depth, float4* __restrict__ out,
+                             int* __restrict__ is_even, int* leaf_cnt, FlatFlags* flags)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    const rt_bvh_node b = nodes[v];
+    if (!is_inner(b)) return;
+    const int k = (b.idx - 1) >> 1;
+    const rt_bvh_node c0 = nodes[b.idx], c1 = nodes[b.idx + 1];
+    const int r0 = child_ref(c0, n_tris, leaf_cnt, flags), r1 = child_ref(c1, n_tris, leaf_cnt, flags);
+    float mn0[3], mx0[3], mn1[3], mx1[3];
+    child_box(c0, r0, mn0, mx0);
+    child_box(c1, r1, mn1, mx1);
+    float4* q = out + 4 * (size_t)k;
+    q[0] = make_float4(mn0[0], mn0[1], mn0[2], mx0[0]);
+    q[1] = make_float4(mx0[1], mx0[2], mn1[0], mn1[1]);
+    q[2] = make_float4(mn1[2], mx1[0], mx1[1], mx1[2]);
+    q[3] = make_float4(__int_as_float(r0), __int_as_float(r1), 0.f, 0.f);
+    is_even[k] = (depth[v] & 1) == 0;
+    atomicMax(&flags->max_depth, (int)depth[v]);
+}
+
+// 4-wide records: the (up to four) grandchildren of an even-depth inner node, a leaf child staying as it is
+__global__ void nodes4_kernel(int n_nodes, int n_tris, const rt_bvh_node* __restrict__ nodes, const unsigned char* __restrict__ depth,
+                              const int* __restrict__ idx4_of, float4* __restrict__ out, unsigned char* __restrict__ lvl4, FlatFlags* flags)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    const rt_bvh_node b = nodes[v];
+    if (!is_inner(b) || (depth[v] & 1)) return;
+    const int k4 = idx4_of[(b.idx - 1) >> 1];
+    int kids[4], c = 0;
+    for (int w = 0; w < 2; w++) {
+        const int ch = b.idx + w;
+        const rt_bvh_node cn = nodes[ch];
+        if (is_inner(cn)) { kids[c++] = cn.idx; kids[c++] = cn.idx + 1; }
+        else kids[c++] = ch;
+    }
+    float q[32];
+    for (int i = 0; i < 24; i++) q[i] = INFINITY;
+    for (int i = 0; i < 4; i++) q[24 + i] = __int_as_float(RT_REF_NONE);
+    for (int i = 28; i < 32; i++) q[i] = 0.f;
+    for (int i = 0; i < c; i++) {
+        const rt_bvh_node kn = nodes[kids[i]];
+        int ref;
+        if (is_inner(kn)) ref = idx4_of[(kn.idx - 1) >> 1];
+        else ref = child_ref(kn, n_tris, nullptr, flags) /* counts were recorded by nodes_kernel */;
+        if (ref == RT_REF_NONE) continue;
+        q[0 + i] = kn.min[0]; q[4 + i] = kn.min[1]; q[8 + i] = kn.min[2];
+        q[12 + i] = kn.max[0]; q[16 + i] = kn.max[1]; q[20 + i] = kn.max[2];
+        q[24 + i] = __int_as_float(ref);
+    }
+    float4* o = out + 8 * (size_t)k4;
+    for (int i = 0; i < 8; i++) o[i] = make_float4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
+    lvl4[k4] = (unsigned char)(depth[v] >> 1);
+}
+
+// stack need of a ray on the 4-wide tree, one level per launch, deepest first: a node with c live children enters one
+// and leaves at most c - 1 pushed (flatten.cpp: need4)
+__global__ void need4_kernel(int n4, const float4* __restrict__ nodes4, const unsigned char* __restrict__ lvl4, int* __restrict__ need4, int level)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n4 || lvl4[k] != level) return;
+    const float4 r = nodes4[8 * (size_t)k + 6];
+    const int ref[4] = {__float_as_int(r.x), __float_as_int(r.y), __float_as_int(r.z), __float_as_int(r.w)};
+    int live = 0, deepest = 0;
+    for (int i = 0; i < 4; i++) {
+        if (ref[i] == RT_REF_NONE) continue;
+        live++;
+        if (ref[i] >= 0) deepest = max(deepest, need4[ref[i]]);
+    }
+    need4[k] = max(live - 1, 0) + deepest;
+}
+
+struct Buf {
+    void* p = nullptr;
+    ~Buf() { cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+    template <class T> T* take() { T* r = static_cast<T*>(p); p = nullptr; return r; }
+};
+
+} // namespace
+
+int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_mats, DeviceFlat& out, std::string& err)
+{
+#define CKF(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { err = std::string("flatten_gpu: ") + #call + " failed: " + cudaGetErrorString(e__); return RT_ERR_CUDA; } } while (0)
+    const int n = (int)t.n_tris, nn = (int)t.n_nodes;
+    if (n < 1 || nn < 3) { err = "flatten_gpu: the tree has no inner node"; return RT_ERR_INVALID; }
+    const size_t n_inner = (size_t)(nn - 1) / 2; // every split allocated two nodes
+    CKF(cudaSetDevice(t.device));
+    Buf tris, shade, nodes, nodes4, leaf_cnt, is_even, idx4, lvl4, need4, flags, mat, scan_tmp;
+    CKF(tris.alloc((size_t)n * 64));
+    CKF(shade.alloc((size_t)n * 16));
+    CKF(nodes.alloc(n_inner * 64));
+    CKF(is_even.alloc(n_inner * 4));
+    CKF(idx4.alloc((n_inner + 1) * 4));
+    CKF(flags.alloc(sizeof(FlatFlags)));
+    CKF(cudaMemset(flags.p, 0, sizeof(FlatFlags)));
+    if (host_tri_mat) {
+        CKF(mat.alloc((size_t)n * 4));
+        CKF(cudaMemcpy(mat.p, host_tri_mat, (size_t)n * 4, cudaMemcpyHostToDevice));
+    }
+    const int B = 256;
+    tris_kernel<<<(n + B - 1) / B, B>>>(n, t.tri, t.tri_idx, tris.as<float4>());
+    shade_kernel<<<(n + B - 1) / B, B>>>(n, t.tri, host_tri_mat ? mat.as<unsigned>() : nullptr, n_mats ? n_mats : 1u, shade.as<float4>(), flags.as<FlatFlags>());
+    nodes_kernel<<<(nn + B - 1) / B, B>>>(nn, n, t.nodes, t.depth, nodes.as<float4>(), is_even.as<int>(), nullptr, flags.as<FlatFlags>());
+    CKF(cudaGetLastError());
+    FlatFlags fl;
+    CKF(cudaMemcpy(&fl, flags.p, sizeof fl, cudaMemcpyDeviceToHost));
+    if (fl.bad_material) { err = "material index out of range"; return RT_ERR_INVALID; }
+    if (fl.bad_leaf) { err = "BVH leaf range out of bounds"; return RT_ERR_INVALID; }
+    if (fl.max_depth + 5 > RT_STACK_ENTRIES) { err = "BVH deeper than the traversal stack (" + std::to_string(fl.max_depth) + ")"; return RT_ERR_INVALID; }
+    if (fl.need_leaf_cnt) { // leaves of >= 15 triangles (depth-capped): second pass fills the side table
+        CKF(leaf_cnt.alloc((size_t)n * 4));
+        CKF(cudaMemset(leaf_cnt.p, 0, (size_t)n * 4));
+        nodes_kernel<<<(nn + B - 1) / B, B>>>(nn, n, t.nodes, t.depth, nodes.as<float4>(), is_even.as<int>(), leaf_cnt.as<int>(), flags.as<FlatFlags>());
+        CKF(cudaGetLastError());
+    }
+    // 4-wide node indices: exclusive scan of the even-depth flags in pre-order
+    size_t tmp_bytes = 0;
+    CKF(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, is_even.as<int>(), idx4.as<int>(), (int)n_inner));
+    CKF(scan_tmp.alloc(tmp_bytes));
+    CKF(cub::DeviceScan::ExclusiveSum(scan_tmp.p, tmp_bytes, is_even.as<int>(), idx4.as<int>(), (int)n_inner));
+    int last_idx = 0, last_flag = 0;
+    CKF(cudaMemcpy(&last_idx, idx4.as<int>() + (n_inner - 1), 4, cudaMemcpyDeviceToHost));
+    CKF(cudaMemcpy(&last_flag, is_even.as<int>() + (n_inner - 1), 4, cudaMemcpyDeviceToHost));
+    const int n4 = last_idx + last_flag;
+    CKF(nodes4.alloc((size_t)n4 * 128));
+    CKF(lvl4.alloc((size_t)n4));
+    CKF(need4.alloc((size_t)n4 * 4));
+    CKF(cudaMemset(need4.p, 0, (size_t)n4 * 4));
+    nodes4_kernel<<<(nn + B - 1) / B, B>>>(nn, n, t.nodes, t.depth, idx4.as<int>(), nodes4.as<float4>(), lvl4.as<unsigned char>(), flags.as<FlatFlags>());
+    for (int level = fl.max_depth / 2; level >= 0; level--)
+        need4_kernel<<<(n4 + B - 1) / B, B>>>(n4, nodes4.as<float4>(), lvl4.as<unsigned char>(), need4.as<int>(), level);
+    CKF(cudaGetLastError());
+    int need_root = 0;
+    CKF(cudaMemcpy(&need_root, need4.p, 4, cudaMemcpyDeviceToHost));
+    CKF(cudaDeviceSynchronize());
+    out.nodes = nodes.take<float4>(); out.nodes4 = nodes4.take<float4>(); out.tris = tris.take<float4>(); out.shade = shade.take<float4>();
+    out.leaf_cnt = fl.need_leaf_cnt ? leaf_cnt.take<int>() : nullptr;
+    out.n_inner = n_inner; out.n_nodes4 = (size_t)n4; out.n_tris = (size_t)n;
+    out.max_depth = fl.max_depth;
+    out.stack_need4 = need_root + 3; // + sentinel, postponed leaf, slack (flatten.cpp)
+#undef CKF
+    return RT_OK;
+}

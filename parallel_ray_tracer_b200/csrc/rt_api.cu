@@ -16,6 +16,7 @@
 #include "camera.h"
 #include "device_layout.h"
 #include "flatten.h"
+#include "gpu_tree.h"
 #include "host_scene.h"
 #include "render_launch.h"
 
@@ -316,32 +317,23 @@ int rt_part_tile_count(int width, int height, int part_index, int part_count)
     return n;
 }
 
-int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** out)
+// Shared tail of rt_create / rt_create_gpu: per-device streams and events, the scene arrays on every device.  `flat` holds
+// the host staging arrays (always mats / lights; nodes, triangles ... only when `pre` is null); `pre` = arrays that are
+// already resident on devices[0] (device-side flatten) and are adopted by the context.
+static int create_common(const rt::FlatScene& flat, rt::DeviceFlat* pre, const int* devices, int ndev, rt_ctx** out)
 {
-    if (!desc || !out) return fail(nullptr, RT_ERR_INVALID, "rt_create: null argument");
-    *out = nullptr;
-    int avail = rt_device_count();
-    if (avail <= 0) return fail(nullptr, RT_ERR_NO_DEVICE, "rt_create: no CUDA device available (this library has no CPU fallback)");
-    int dflt = 0;
-    if (!devices || ndev <= 0) { devices = &dflt; ndev = 1; }
-    if (ndev > RT_MAX_DEVICES) return fail(nullptr, RT_ERR_INVALID, "rt_create: too many devices");
-    for (int i = 0; i < ndev; i++)
-        if (devices[i] < 0 || devices[i] >= avail) return fail(nullptr, RT_ERR_INVALID, "rt_create: device index out of range");
-
-    rt::FlatScene flat;
-    std::string err;
-    int rc = rt::flatten_scene(*desc, flat, err);
-    if (rc) return fail(nullptr, rc, "rt_create: " + err);
-
     rt_ctx* c = new rt_ctx();
-    c->scene_bytes = flat.bytes();
-    c->max_depth = flat.max_depth;
-    c->stack_need4 = flat.stack_need4;
+    c->scene_bytes = pre ? pre->bytes() + 4 * (flat.mats.size() + flat.lights.size()) : flat.bytes();
+    c->max_depth = pre ? pre->max_depth : flat.max_depth;
+    c->stack_need4 = pre ? pre->stack_need4 : flat.stack_need4;
     c->scene_host_view.n_lights = (int)flat.n_lights;
     std::memcpy(c->scene_host_view.amb, flat.ambient, 12);
     c->devs.resize(ndev);
     auto bail = [&](int code) { std::string m = c->err; rt_destroy(c); rt::set_error(m); return code; };
 #define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { c->err = std::string(#call) + " failed: " + cudaGetErrorString(e__); return bail(RT_ERR_CUDA); } } while (0)
+    const size_t b_nodes = pre ? 64 * pre->n_inner : flat.nodes.size() * 4, b_nodes4 = pre ? 128 * pre->n_nodes4 : flat.nodes4.size() * 4;
+    const size_t b_tris = pre ? 64 * pre->n_tris : flat.tris.size() * 4, b_shade = pre ? 16 * pre->n_tris : flat.shade.size() * 4;
+    const size_t b_leaf = pre ? (pre->leaf_cnt ? 4 * pre->n_tris : 0) : flat.leaf_cnt.size() * 4;
     for (int i = 0; i < ndev; i++) {
         Dev& D = c->devs[i];
         D.id = devices[i];
@@ -367,13 +359,18 @@ int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** 
             return cudaMemcpyPeerAsync(*dst, D.id, *src0, c->devs[0].id, bytes, D.stream);
         };
         Dev& Z = c->devs[0];
-        CKC(put(&D.nodes, flat.nodes.data(), &Z.nodes, flat.nodes.size() * 4));
-        CKC(put(&D.nodes4, flat.nodes4.data(), &Z.nodes4, flat.nodes4.size() * 4));
-        CKC(put(&D.tris, flat.tris.data(), &Z.tris, flat.tris.size() * 4));
-        CKC(put(&D.shade, flat.shade.data(), &Z.shade, flat.shade.size() * 4));
+        if (i == 0 && pre) { // adopt the arrays the device-side flatten left on this device
+            D.nodes = pre->nodes; D.nodes4 = pre->nodes4; D.tris = pre->tris; D.shade = pre->shade; D.leaf_cnt = pre->leaf_cnt;
+            pre->nodes = pre->nodes4 = pre->tris = pre->shade = nullptr; pre->leaf_cnt = nullptr;
+        } else {
+            CKC(put(&D.nodes, flat.nodes.data(), &Z.nodes, b_nodes));
+            CKC(put(&D.nodes4, flat.nodes4.data(), &Z.nodes4, b_nodes4));
+            CKC(put(&D.tris, flat.tris.data(), &Z.tris, b_tris));
+            CKC(put(&D.shade, flat.shade.data(), &Z.shade, b_shade));
+            CKC(put(&D.leaf_cnt, flat.leaf_cnt.data(), &Z.leaf_cnt, b_leaf));
+        }
         CKC(put(&D.mats, flat.mats.data(), &Z.mats, flat.mats.size() * 4));
         CKC(put(&D.lights, flat.lights.data(), &Z.lights, flat.lights.size() * 4));
-        CKC(put(&D.leaf_cnt, flat.leaf_cnt.data(), &Z.leaf_cnt, flat.leaf_cnt.size() * 4));
         CKC(cudaMalloc((void**)&D.ctrl, 8 * RT_CTRL_WORDS * RT_FRAME_SLOTS));
         CKC(cudaMallocHost((void**)&D.ctrl_host, 64 * RT_FRAME_SLOTS));
         CKC(cudaStreamSynchronize(D.stream));
@@ -391,6 +388,70 @@ int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** 
 #undef CKC
     *out = c;
     return RT_OK;
+}
+
+static int check_devices(const char* who, const int*& devices, int& ndev, const int* dflt)
+{
+    int avail = rt_device_count();
+    if (avail <= 0) return fail(nullptr, RT_ERR_NO_DEVICE, std::string(who) + ": no CUDA device available (this library has no CPU fallback)");
+    if (!devices || ndev <= 0) { devices = dflt; ndev = 1; }
+    if (ndev > RT_MAX_DEVICES) return fail(nullptr, RT_ERR_INVALID, std::string(who) + ": too many devices");
+    for (int i = 0; i < ndev; i++)
+        if (devices[i] < 0 || devices[i] >= avail) return fail(nullptr, RT_ERR_INVALID, std::string(who) + ": device index out of range");
+    return RT_OK;
+}
+
+int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** out)
+{
+    if (!desc || !out) return fail(nullptr, RT_ERR_INVALID, "rt_create: null argument");
+    *out = nullptr;
+    const int dflt = 0;
+    int rc = check_devices("rt_create", devices, ndev, &dflt);
+    if (rc) return rc;
+    rt::FlatScene flat;
+    std::string err;
+    rc = rt::flatten_scene(*desc, flat, err);
+    if (rc) return fail(nullptr, rc, "rt_create: " + err);
+    return create_common(flat, nullptr, devices, ndev, out);
+}
+
+// Triangles -> render-ready context without the tree visiting the host: heuristic-6 BVH built on devices[0]
+// (bvh_build_gpu.cu), flattened there (flatten_gpu.cu), fanned out to the other devices over NVLink.
+int rt_create_gpu(rt_scene* s, int heuristic, const int* devices, int ndev, int download_tree, rt_ctx** out, rt_bvh_gpu_stats* stats)
+{
+    if (stats) std::memset(stats, 0, sizeof *stats);
+    if (!s || !out) return fail(nullptr, RT_ERR_INVALID, "rt_create_gpu: null argument");
+    *out = nullptr;
+    if ((heuristic & ~RT_BVH_REFBIN) != 6) return fail(nullptr, RT_ERR_INVALID, "rt_create_gpu: only heuristic 6 is built on the GPU");
+    const int dflt = 0;
+    int rc = check_devices("rt_create_gpu", devices, ndev, &dflt);
+    if (rc) return rc;
+    rt_scene_desc d;
+    rt::GpuTree tree;
+    const bool tiny = s->n_tris() <= 2; // the root is a leaf: flatten.cpp's synthetic root node
+    if (!tiny) {
+        rc = rt::gpu_build_bvh(*s, (heuristic & RT_BVH_REFBIN) ? 1 : 0, devices[0], stats, download_tree ? nullptr : &tree);
+        if (rc) return rc;
+    } else if ((rc = rt_scene_build_bvh(s, heuristic))) return rc;
+    if (tiny || download_tree || tree.fell_back) { // the tree is on the host (asked for, or degenerate input): host flatten
+        if ((rc = rt_scene_view(s, &d))) return rc;
+        return rt_create(&d, devices, ndev, out);
+    }
+    s->bvh.clear(); s->tri_idx.clear(); // the host scene has no tree in this mode
+    if ((rc = rt_scene_view(s, &d))) return rc;
+    rt::FlatScene small;
+    rt::flatten_small(d, small);
+    rt::DeviceFlat df;
+    std::string err;
+    rc = rt::flatten_gpu(tree, s->tri_mat.empty() ? nullptr : s->tri_mat.data(), s->n_mats(), df, err);
+    tree.release();
+    if (rc) {
+        cudaFree(df.nodes); cudaFree(df.nodes4); cudaFree(df.tris); cudaFree(df.shade); cudaFree(df.leaf_cnt);
+        return fail(nullptr, rc, "rt_create_gpu: " + err);
+    }
+    rc = create_common(small, &df, devices, ndev, out);
+    cudaFree(df.nodes); cudaFree(df.nodes4); cudaFree(df.tris); cudaFree(df.shade); cudaFree(df.leaf_cnt); // (null once adopted)
+    return rc;
 }
 
 void rt_destroy(rt_ctx* c)

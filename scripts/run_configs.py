@@ -111,6 +111,18 @@ def main():
              "kernel_ms": ms, "rays": rays, "mrays_s": rays / ms / 1e3,
              "algorithmic_bytes": 64 * tmw.inner_visits + 40 * tmw.tri_tests, "algorithmic_gbs": (64 * tmw.inner_visits + 40 * tmw.tri_tests) / ms / 1e6,
              "fast_vs_strict": parity(ctx, 3840, 2160)})
+        # triangles -> render-ready context entirely on the device (rt_create_gpu: GPU build + GPU flatten, no host round trip)
+        ctx.render_frame(rt.default_params(width=3840, height=2160))
+        want = ctx.load_from_gpu()["bgra"].copy()
+        ctx.close(); big.close()
+        big2 = base.instance_grid(39, 40, 1, (11.5, 6.5, 3.0))
+        tp0 = time.perf_counter()
+        ctx2 = rt.Context.build_on_gpu(big2, [0])
+        tp1 = time.perf_counter()
+        ctx2.render_frame(rt.default_params(width=3840, height=2160))
+        same = bool(np.array_equal(ctx2.load_from_gpu()["bgra"], want))
+        out({"config": 5, "device_pipeline": {"triangles_to_context_s": tp1 - tp0, "build_ms": ctx2.build_stats.total_ms, "frame_equals_host_path": same}})
+        ctx2.close(); big2.close()
 
 
 if __name__ == "__main__":
