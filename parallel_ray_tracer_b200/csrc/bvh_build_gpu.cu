@@ -518,9 +518,9 @@ __global__ void __launch_bounds__(kSubWarps * 32) subtree_kernel(int n_sub, cons
                 const float4 a = info[3 * (size_t)ti];
                 const float cen = splitAxis == 0 ? a.x : (splitAxis == 1 ? a.y : a.z);
                 if (cen < splitPos) continue;
-                int p = i; // chains are at most n_el < kMid long
-                while (p < nl) p = posL[first + p];
-                tmp[first + p] = ti;
+                int p = i, steps = 0; // a chain visits every position at most once: <= n_el steps
+                while (p < nl && steps++ <= n_el) p = posL[first + p];
+                if (p >= nl) tmp[first + p] = ti; else flags->chain_overflow = 1;
             }
             __syncwarp();
             for (int i = lane; i < n_el; i += 32) tri_idx[first + i] = tmp[first + i];
@@ -626,7 +626,7 @@ int rt::gpu_build_bvh(rt_scene& scene, int refbin, int device, rt_bvh_gpu_stats*
     int kSmall = kSmallDefault;
     if (const char* e = std::getenv("RT_BVH_GPU_SMALL")) { const int v = std::atoi(e); if (v >= 3 && v <= (1 << 20)) kSmall = v; }
     const size_t max_active = n / (size_t)kSmall + 2;
-    const size_t max_top_nodes = 4 * max_active + 64; // every top split has >= kSmall triangles: <= n / kSmall splits per level chain... bounded below
+    const size_t max_top_nodes = 4 * max_active + 64; // first allocation; the node array grows on demand (lopsided splits)
     CKB(d_tri.alloc(n * 36));
     CKB(d_info.alloc(n * 48));
     CKB(d_idx.alloc(n * 4));

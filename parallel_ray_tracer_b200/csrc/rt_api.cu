@@ -887,33 +887,35 @@ int rt_debug_gather_bandwidth(int device, size_t ws_bytes, float* gbs_out)
     size_t n_rec = 1;
     while (n_rec * 2 * 64 <= ws_bytes) n_rec *= 2;
     if (n_rec > (1ull << 31)) n_rec = 1ull << 31;
-    rt_ctx* c = nullptr; // (CK needs a context pointer only for the error text)
-    rt_ctx dummy;
-    c = &dummy;
-    CK(c, cudaSetDevice(device));
-    float4* data = nullptr;
-    float4* sink = nullptr;
-    CK(c, cudaMalloc((void**)&data, n_rec * 64));
-    CK(c, cudaMalloc((void**)&sink, 64));
-    CK(c, cudaMemset(data, 0, n_rec * 64));
-    cudaDeviceProp prop;
-    CK(c, cudaGetDeviceProperties(&prop, device));
-    const int grid = prop.multiProcessorCount * 8, block = 256, iters = 512;
-    cudaEvent_t e0, e1;
-    CK(c, cudaEventCreate(&e0)); CK(c, cudaEventCreate(&e1));
+    float4 *data = nullptr, *sink = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     float best = 0.f;
-    for (int rep = 0; rep < 3; rep++) { // rep 0 warms the caches / clocks
-        CK(c, cudaEventRecord(e0));
-        gather64_kernel<<<grid, block>>>(data, (unsigned)(n_rec - 1), iters, 12345u + rep, sink);
-        CK(c, cudaEventRecord(e1));
-        CK(c, cudaEventSynchronize(e1));
-        float ms = 0.f;
-        CK(c, cudaEventElapsedTime(&ms, e0, e1));
-        const float gbs = (float)((double)grid * block * iters * 64.0 / (ms * 1e-3) / 1e9);
-        if (rep > 0 && gbs > best) best = gbs;
-    }
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    auto run = [&]() -> cudaError_t {
+        cudaError_t e;
+        if ((e = cudaSetDevice(device)) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void**)&data, n_rec * 64)) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void**)&sink, 64)) != cudaSuccess) return e;
+        if ((e = cudaMemset(data, 0, n_rec * 64)) != cudaSuccess) return e;
+        cudaDeviceProp prop;
+        if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return e;
+        const int grid = prop.multiProcessorCount * 8, block = 256, iters = 512;
+        if ((e = cudaEventCreate(&e0)) != cudaSuccess || (e = cudaEventCreate(&e1)) != cudaSuccess) return e;
+        for (int rep = 0; rep < 3; rep++) { // rep 0 warms the caches / clocks
+            if ((e = cudaEventRecord(e0)) != cudaSuccess) return e;
+            gather64_kernel<<<grid, block>>>(data, (unsigned)(n_rec - 1), iters, 12345u + rep, sink);
+            if ((e = cudaEventRecord(e1)) != cudaSuccess || (e = cudaEventSynchronize(e1)) != cudaSuccess) return e;
+            float ms = 0.f;
+            if ((e = cudaEventElapsedTime(&ms, e0, e1)) != cudaSuccess) return e;
+            const float gbs = (float)((double)grid * block * iters * 64.0 / (ms * 1e-3) / 1e9);
+            if (rep > 0 && gbs > best) best = gbs;
+        }
+        return cudaSuccess;
+    };
+    const cudaError_t e = run();
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
     cudaFree(data); cudaFree(sink);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, RT_ERR_CUDA, std::string("rt_debug_gather_bandwidth: ") + cudaGetErrorString(e)); }
     *gbs_out = best;
     return RT_OK;
 }
