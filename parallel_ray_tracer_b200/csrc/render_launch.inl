@@ -9,6 +9,10 @@ template <bool WORK, bool SPEC, bool WIDE>
 static kernel_fn pick(int block, int minb)
 {
     if (block == 64) return render_kernel<64, 12, WORK, SPEC, WIDE>;
+#if RT_OPT_PARK
+    if (minb >= 10) return render_kernel<128, 10, WORK, SPEC, WIDE>;
+    if (minb >= 9) return render_kernel<128, 9, WORK, SPEC, WIDE>;
+#endif
     if (minb >= 8) return render_kernel<128, 8, WORK, SPEC, WIDE>;
     if (minb >= 7) return render_kernel<128, 7, WORK, SPEC, WIDE>;
     if (minb >= 6) return render_kernel<128, 6, WORK, SPEC, WIDE>;

@@ -533,14 +533,14 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
     RtLaunchCfg cfg;
     cfg.block_threads = p->block_threads == 64 ? 64 : 128;
     // Defaults (profiles/r01_notes.md): small frames are bounded by the dependent chain of their longest pixels, which the
-    // 4-wide tree halves; large frames are throughput-bound, where the 2-wide tree with 28 warps/SM (72 registers) wins.
+    // 4-wide tree halves; large frames are throughput-bound, where the 2-wide tree with 32 warps/SM (64 registers) wins.
     // "Small" is decided by the rays the previous frame of the same shape actually traced on this context (8 M per GPU),
     // and by the pixel-sample count (4 M per GPU) for a first frame.
     const double px_per_part = (double)w * h * p->spp / (double)(part_count * (int)c->devs.size());
     const bool same_shape = c->rays_w == w && c->rays_h == h && c->rays_spp == p->spp && c->rays_parts == part_count;
     const bool small_frame = same_shape ? c->rays_per_dev <= 8.0e6 : px_per_part <= 4.0e6;
     const bool want_wide = p->traversal == RT_TRAVERSAL_WIDE || (p->traversal == RT_TRAVERSAL_DEFAULT && small_frame);
-    cfg.min_ctas = p->ctas_per_sm > 0 ? p->ctas_per_sm : (cfg.block_threads == 64 ? 12 : (want_wide ? 6 : 7));
+    cfg.min_ctas = p->ctas_per_sm > 0 ? p->ctas_per_sm : (cfg.block_threads == 64 ? 12 : (want_wide ? 6 : 8));
     cfg.work_counters = (p->aov_mask & RT_AOV_WORK) != 0;
     cfg.speculative = p->traversal != RT_TRAVERSAL_PLAIN;
     // (the 4-wide tree is only used when its worst-case stack need fits the shared stack)

@@ -9,6 +9,6 @@ $CMD > gpurun_out/plain2_$T.log 2> gpurun_out/plain2_$T.err &&
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:rt_fast::render_kernel<.int.128, .int.6, .bool.0, .bool.1, .bool.1>" -s 6 -c 1 \
     -f -o gpurun_out/prof_${T}_car_only $CMD > gpurun_out/ncu_f_$T.log 2>&1
 $CMD > gpurun_out/plain3_$T.log 2> gpurun_out/plain3_$T.err &&
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:rt_fast::render_kernel<.int.128, .int.7, .bool.0, .bool.1, .bool.0>" -s 4 -c 1 \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:rt_fast::render_kernel<.int.128, .int.8, .bool.0, .bool.1, .bool.0>" -s 4 -c 1 \
     -f -o gpurun_out/prof_${T}_car_boxed_4k $CMD > gpurun_out/ncu_g_$T.log 2>&1
 ls -la gpurun_out/*$T*
