@@ -75,7 +75,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -335,6 +335,31 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
     torch.cuda.synchronize(); barrier()
     e2e_sync_ms = (time.perf_counter() - t_s0) * 1e3 / args.steps
 
+    # ---- frame sequences across GPUs: alternate-frame rendering (every rank renders WHOLE frames of the sequence, its own
+    # copy stream, no frame assembly) — the weak-scaling counterpart of the tile split above, reported beside it ----
+    afr = None
+    if world > 1:
+        full = [rt.default_params(width=W, height=H, spp=SPP, frame_slot=s) for s in range(rt.RT_FRAME_SLOTS)]
+        ctx_full = rt.Context(sc, [local])   # a context without the imported frame: renders into its own slots
+
+        def afr_loop(steps):
+            for k in range(steps):
+                s = k % rt.RT_FRAME_SLOTS
+                if k >= rt.RT_FRAME_SLOTS:
+                    ctx_full.frame_wait(s)
+                ctx_full.render_frame_async(full[s])
+                ctx_full.download_async(s, pinned[s].data_ptr())
+            for s in range(min(steps, rt.RT_FRAME_SLOTS)):
+                ctx_full.frame_wait(s)
+        afr_loop(4)
+        barrier(); torch.cuda.synchronize()
+        t_a0 = time.perf_counter()
+        afr_loop(args.steps)
+        torch.cuda.synchronize(); barrier()
+        afr_ms = (time.perf_counter() - t_a0) * 1e3
+        afr = (afr_ms,)
+        ctx_full.close()
+
     # ---- reductions over ranks ----
     def allmax(x):
         if world == 1: return x
@@ -350,6 +375,7 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
     wall_ms = allmax(wall_ms)
     e2e_ms = allmax(e2e_ms)
     e2e_sync_ms = allmax(e2e_sync_ms)
+    afr_ms = allmax(afr[0]) if afr else None
     rays = int(allsum(rays_local))
     launches = int(allsum(launches))
 
@@ -458,6 +484,10 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
                                            "L1 hit rate 95-98 % (profiles/), so the L1 figure is the bound that applies"},
                "roofline_fp32": {"achieved_tlaneops": fp_ach, "peak_tlaneops": fp_peak, "frac": fp_ach / fp_peak,
                                  "note": "48 flops x inner visits + 54 x triangle tests vs 148 SM x 128 lanes x max SM clock"},
+               "sequence_afr": (None if afr_ms is None else {
+                   "value": rays * world * args.steps / afr_ms / 1e3, "unit": METRIC, "frames": world * args.steps, "ms_total": afr_ms, "scaling": "weak",
+                   "note": "alternate-frame rendering of a frame sequence: every rank renders whole frames (K each) and copies them to its own "
+                           "pinned host buffer; no frame assembly.  Reported beside the tile-split numbers, not instead of them"}),
                "also": also,
                "work": {"inner_visits": inner, "tri_tests": tris,
                         "note": "reference visit order (strict build counters == oracle counters, tests/test_gpu_parity.py)"}}
