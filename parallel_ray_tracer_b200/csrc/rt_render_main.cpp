@@ -19,6 +19,7 @@ static void usage()
     std::printf("usage: rt_render (--scene-dir DIR | --rtsc FILE | --soup N) [--width W] [--height H] [--spp S] [--seed K]\n"
                 "                 [--bounces B] [--heuristic 6|0|1] [--refbin-tree] [--strict] [--gpus N] [--iterations I] [--warmup W]\n"
                 "                 [--cam px py pz rx ry rz fov] [--out FILE.bmp] [--ctas-per-sm C] [--block T] [--refill R] [--peer-copy]\n"
+                "                 [--gpu-build]   build the BVH and lay the scene out on the GPU (rt_create_gpu) instead of the host\n"
                 "                 [--sequence N [--spin DZ]]   N frames end to end (camera rot.z += DZ per frame), each copied to the host\n"
                 "                                              while the next one renders; the last one is written bottom-up as the BMP\n");
 }
@@ -29,6 +30,7 @@ int main(int argc, char** argv)
     int soup = 0, heuristic = 6, gpus = 1, iterations = 100, warmup = 50; // gpu/include/options.cuh:25-26
     int sequence = 0;
     float spin = 0.0f;
+    bool gpu_build = false;
     rt_render_params p;
     rt_render_params_default(&p);
     for (int i = 1; i < argc; i++) {
@@ -53,6 +55,7 @@ int main(int argc, char** argv)
         else if (a == "--block") p.block_threads = std::atoi(next());
         else if (a == "--refill") p.refill_threshold = std::atoi(next());
         else if (a == "--peer-copy") p.gather = RT_GATHER_PEER_COPY;
+        else if (a == "--gpu-build") gpu_build = true;
         else if (a == "--sequence") sequence = std::atoi(next());
         else if (a == "--spin") spin = (float)std::atof(next());
         else if (a == "--cam") {
@@ -69,17 +72,26 @@ int main(int argc, char** argv)
     else if (soup > 0) rc = rt_scene_soup((uint32_t)soup, 1, &sc);
     else { usage(); return 2; }
     if (rc) { std::fprintf(stderr, "%s\n", rt_last_error(nullptr)); return 1; }
-    std::printf("Building BVH...\n");
-    if ((rc = rt_scene_build_bvh(sc, heuristic))) { std::fprintf(stderr, "%s\n", rt_last_error(nullptr)); return 1; }
-    rt_scene_desc d;
-    rt_scene_view(sc, &d);
-    std::printf("\n# Scene complexity #\nResolution: %d x %d\nNumber of triangles: %u\nNumber of lights: %u\nNumber of ray bounces: %d\nBVH nodes: %u\n",
-                p.width, p.height, d.n_tris, d.n_lights, p.bounces, d.bvh_len);
-
     std::vector<int> devs(gpus);
     for (int i = 0; i < gpus; i++) devs[i] = i;
     rt_ctx* ctx = nullptr;
-    if ((rc = rt_create(&d, devs.data(), gpus, &ctx))) { std::fprintf(stderr, "%s\n", rt_last_error(nullptr)); return 1; }
+    rt_scene_desc d;
+    std::printf("Building BVH...\n");
+    if (gpu_build) {
+        // bvh_build + load_to_gpu in one step on the device (cpu/src/main.c:138, gpu/src/main.cu:98-110)
+        rt_bvh_gpu_stats st;
+        if ((rc = rt_create_gpu(sc, heuristic, devs.data(), gpus, 0, &ctx, &st))) { std::fprintf(stderr, "%s\n", rt_last_error(nullptr)); return 1; }
+        rt_scene_view(sc, &d);
+        std::printf("BVH built on the GPU in %.2f ms (%u nodes, %d level passes, %d subtrees%s)\n", st.total_ms, st.nodes, st.levels, st.subtrees,
+                    st.fell_back ? ", host fallback" : "");
+        d.bvh_len = st.nodes;
+    } else {
+        if ((rc = rt_scene_build_bvh(sc, heuristic))) { std::fprintf(stderr, "%s\n", rt_last_error(nullptr)); return 1; }
+        rt_scene_view(sc, &d);
+    }
+    std::printf("\n# Scene complexity #\nResolution: %d x %d\nNumber of triangles: %u\nNumber of lights: %u\nNumber of ray bounces: %d\nBVH nodes: %u\n",
+                p.width, p.height, d.n_tris, d.n_lights, p.bounces, d.bvh_len);
+    if (!ctx && (rc = rt_create(&d, devs.data(), gpus, &ctx))) { std::fprintf(stderr, "%s\n", rt_last_error(nullptr)); return 1; }
 
     std::printf("\nRendering...\n");
     std::vector<double> times;

@@ -266,6 +266,12 @@ def test_cpp_host_driver_writes_the_reference_bmp(rt, oracle_scenes, tmp_path):
     rows = np.frombuffer(raw, np.uint8, 4 * 320 * 180, 54).reshape(180, 320, 4)[::-1]
     ref = oracle_scenes["car_only"].render(320, 180)
     assert np.array_equal(rows, ref["bgra"])
+    # --gpu-build: BVH build + scene layout on the device, same file
+    out2 = tmp_path / "g.bmp"
+    r = subprocess.run([str(exe), "--rtsc", str(O.HERE.parent / "tests" / "golden" / "scenes" / "car_only.rtsc"), "--width", "320", "--height", "180",
+                        "--strict", "--iterations", "2", "--warmup", "1", "--out", str(out2), "--gpu-build"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "BVH built on the GPU" in r.stdout, r.stdout + r.stderr
+    assert out2.read_bytes() == raw
 
 
 def test_error_paths(rt, gpu_scenes):
