@@ -18,7 +18,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "host_scene.h"
@@ -47,7 +49,7 @@ struct Material { char name[256]; float kd[3], ks[3], kr[3]; };
 
 extern "C" {
 
-int rt_scene_load_obj(const char* obj_path, const char* mtl_path, const char* lights_path, rt_scene** out)
+static int load_obj_serial(const char* obj_path, const char* mtl_path, const char* lights_path, rt_scene** out)
 {
     if (!obj_path || !mtl_path || !out) { rt::set_error("rt_scene_load_obj: null argument"); return RT_ERR_INVALID; }
     std::vector<std::string> obj, mtl;
@@ -106,6 +108,234 @@ int rt_scene_load_obj(const char* obj_path, const char* mtl_path, const char* li
             for (int k = 0; k < 3; k++) sc->tri.insert(sc->tri.end(), &verts[3 * (size_t)(v[k] - 1)], &verts[3 * (size_t)(v[k] - 1)] + 3);
             sc->tri_mat.push_back(current);
         }
+    }
+
+    if (lights_path) {
+        std::vector<std::string> ll;
+        if (!read_lines(lights_path, ll)) {
+            rt::set_error(std::string("cannot open ") + lights_path);
+            delete sc;
+            return RT_ERR_IO;
+        }
+        for (const std::string& l : ll) {
+            float v[6];
+            if (std::sscanf(l.c_str(), "%f %f %f %f %f %f", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]) == 6)
+                sc->lights.insert(sc->lights.end(), v, v + 6);
+        }
+    }
+    *out = sc;
+    return RT_OK;
+}
+
+} // extern "C"
+
+// ---- the same loader at memory speed: one read of the file, line index, lines parsed on all host threads ----
+// Semantics are those of the line-by-line version above (which stays as the checker: RT_LOADER_SERIAL=1, and
+// tests/test_scene_host.py compares the two): lines are what fgets(buf, 256) would return (at most 255 characters,
+// cut after a newline, text after a NUL ignored), "v " lines give up to three floats (missing ones are 0), any line
+// starting with 'f' must give three in-range vertex numbers, "usemtl" switches the current material by exact name and
+// an unknown name keeps the previous one.  Vertices may be defined after the faces that use them (two passes).
+namespace {
+
+struct LineRef { size_t pos; uint32_t len; };
+
+bool read_file(const char* path, std::string& out)
+{
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return false;
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    out.resize(sz > 0 ? (size_t)sz : 0);
+    const bool ok = out.empty() || std::fread(&out[0], 1, out.size(), f) == out.size();
+    std::fclose(f);
+    return ok;
+}
+
+void split_lines(const std::string& data, std::vector<LineRef>& lines)
+{
+    const char* base = data.data();
+    size_t pos = 0;
+    const size_t n = data.size();
+    while (pos < n) {
+        const size_t maxend = std::min(pos + 255, n);
+        const void* nl = std::memchr(base + pos, '\n', maxend - pos);
+        const size_t end = nl ? (size_t)((const char*)nl - base) + 1 : maxend;
+        lines.push_back({pos, (uint32_t)(end - pos)});
+        pos = end;
+    }
+}
+
+// copy of one line as the C string the serial loader sees (NUL-terminated, cut at an embedded NUL)
+inline void line_cstr(const std::string& data, const LineRef& l, char* buf)
+{
+    std::memcpy(buf, data.data() + l.pos, l.len);
+    buf[l.len] = 0;
+}
+
+// sscanf(s, "%f %f %f") after a literal prefix: up to three floats, stop at the first that does not parse
+inline int scan_floats(const char* s, float* v, int n)
+{
+    int got = 0;
+    for (; got < n; got++) {
+        char* end;
+        const float x = std::strtof(s, &end);
+        if (end == s) break;
+        v[got] = x;
+        s = end;
+    }
+    return got;
+}
+
+inline int scan_ints(const char* s, int* v, int n)
+{
+    int got = 0;
+    for (; got < n; got++) {
+        char* end;
+        const long x = std::strtol(s, &end, 10);
+        if (end == s) break;
+        v[got] = (int)x;
+        s = end;
+    }
+    return got;
+}
+
+struct ObjItem { uint32_t line; int kind; int v[3]; }; // kind 0 = face, 1 = usemtl (v[0] = index into names), 2 = bad face
+
+template <class F>
+void run_chunks(size_t count, size_t chunks, F f)
+{
+    if (chunks <= 1) { f(0, (size_t)0, count); return; }
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < chunks; i++) th.emplace_back([=] { f(i, count * i / chunks, count * (i + 1) / chunks); });
+    for (auto& x : th) x.join();
+}
+
+} // namespace
+
+extern "C" {
+
+int rt_scene_load_obj(const char* obj_path, const char* mtl_path, const char* lights_path, rt_scene** out)
+{
+    if (!obj_path || !mtl_path || !out) { rt::set_error("rt_scene_load_obj: null argument"); return RT_ERR_INVALID; }
+    if (const char* e = std::getenv("RT_LOADER_SERIAL")) if (e[0] == '1') return load_obj_serial(obj_path, mtl_path, lights_path, out);
+    std::string data;
+    if (!read_file(obj_path, data)) { rt::set_error(std::string("cannot load ") + obj_path); return RT_ERR_IO; }
+    std::vector<std::string> mtl;
+    if (!read_lines(mtl_path, mtl)) { rt::set_error(std::string("cannot load ") + mtl_path); return RT_ERR_IO; }
+    std::vector<LineRef> lines;
+    split_lines(data, lines);
+
+    // materials: a handful of lines, as in the serial loader
+    std::vector<Material> mats;
+    for (size_t i = 0; i < mtl.size(); i++) {
+        if (std::strncmp(mtl[i].c_str(), "newmtl", 6) == 0 && mats.size() < 128) {
+            Material m;
+            std::memset(&m, 0, sizeof m);
+            std::sscanf(mtl[i].c_str(), "newmtl %255s", m.name);
+            for (size_t j = i + 1; j < i + 6 && j < mtl.size(); j++) {
+                const char* s = mtl[j].c_str();
+                if (std::strncmp(s, "Kd", 2) == 0) std::sscanf(s, "Kd %f %f %f", &m.kd[0], &m.kd[1], &m.kd[2]);
+                else if (std::strncmp(s, "Ks", 2) == 0) std::sscanf(s, "Ks %f %f %f", &m.ks[0], &m.ks[1], &m.ks[2]);
+                else if (std::strncmp(s, "Kr", 2) == 0) std::sscanf(s, "Kr %f %f %f", &m.kr[0], &m.kr[1], &m.kr[2]);
+            }
+            mats.push_back(m);
+        }
+    }
+
+    size_t chunks = 1;
+    {
+        const char* e = std::getenv("RT_LOADER_CHUNKS"); // tests force many small chunks
+        const size_t hw = e ? (size_t)std::atoi(e) : (size_t)std::thread::hardware_concurrency();
+        chunks = std::max<size_t>(1, std::min(hw ? hw : 1, e ? lines.size() : lines.size() / 4096));
+    }
+    std::vector<std::vector<float>> cverts(chunks);
+    std::vector<std::vector<ObjItem>> citems(chunks);
+    std::vector<std::vector<std::string>> cnames(chunks);
+    run_chunks(lines.size(), chunks, [&](size_t c, size_t lo, size_t hi) {
+        char buf[256];
+        for (size_t i = lo; i < hi; i++) {
+            const char* p = data.data() + lines[i].pos;
+            const uint32_t len = lines[i].len;
+            if (len >= 2 && p[0] == 'v' && p[1] == ' ') {
+                line_cstr(data, lines[i], buf);
+                float v[3] = {0, 0, 0};
+                scan_floats(buf + 1, v, 3);
+                cverts[c].insert(cverts[c].end(), v, v + 3);
+            } else if (len >= 6 && std::memcmp(p, "usemtl", 6) == 0) {
+                line_cstr(data, lines[i], buf);
+                char name[256] = {0};
+                std::sscanf(buf, "usemtl %255s", name);
+                cnames[c].push_back(name);
+                citems[c].push_back({(uint32_t)i, 1, {(int)cnames[c].size() - 1, 0, 0}});
+            } else if (len >= 1 && p[0] == 'f') {
+                line_cstr(data, lines[i], buf);
+                ObjItem it{(uint32_t)i, 0, {0, 0, 0}};
+                if (scan_ints(buf + 1, it.v, 3) != 3) it.kind = 2;
+                citems[c].push_back(it);
+            }
+        }
+    });
+    std::vector<float> verts;
+    {
+        size_t total = 0;
+        for (auto& v : cverts) total += v.size();
+        verts.reserve(total);
+        for (auto& v : cverts) verts.insert(verts.end(), v.begin(), v.end());
+    }
+    const int nv = (int)(verts.size() / 3);
+
+    // current material at the start of every chunk (serial over the few usemtl lines), face offsets
+    std::vector<uint32_t> carry(chunks + 1, 0);
+    std::vector<size_t> face_off(chunks + 1, 0);
+    auto resolve = [&](const std::string& name, uint32_t cur) {
+        for (size_t m = 0; m < mats.size(); m++)
+            if (std::strcmp(name.c_str(), mats[m].name) == 0) return (uint32_t)m + 1;
+        return cur; // an unknown name keeps the previous material (triangle.c:97-108)
+    };
+    for (size_t c = 0; c < chunks; c++) {
+        uint32_t cur = carry[c];
+        size_t faces = 0;
+        for (const ObjItem& it : citems[c]) {
+            if (it.kind == 1) cur = resolve(cnames[c][(size_t)it.v[0]], cur);
+            else faces++;
+        }
+        carry[c + 1] = cur;
+        face_off[c + 1] = face_off[c] + faces;
+    }
+
+    rt_scene* sc = new rt_scene();
+    // material 0 = the all-zero "no usemtl yet" material (current_ks/kd/kr = {0}, triangle.c:92)
+    sc->mats.assign(9, 0.0f);
+    for (const Material& m : mats) {
+        sc->mats.insert(sc->mats.end(), m.ks, m.ks + 3);
+        sc->mats.insert(sc->mats.end(), m.kd, m.kd + 3);
+        sc->mats.insert(sc->mats.end(), m.kr, m.kr + 3);
+    }
+    sc->tri.resize(9 * face_off[chunks]);
+    sc->tri_mat.resize(face_off[chunks]);
+    std::vector<uint32_t> first_bad(chunks, UINT32_MAX);
+    run_chunks(chunks, chunks, [&](size_t, size_t lo, size_t hi) {
+        for (size_t c = lo; c < hi; c++) {
+            uint32_t cur = carry[c];
+            size_t f = face_off[c];
+            for (const ObjItem& it : citems[c]) {
+                if (it.kind == 1) { cur = resolve(cnames[c][(size_t)it.v[0]], cur); continue; }
+                const int* v = it.v;
+                if (it.kind == 2 || v[0] < 1 || v[1] < 1 || v[2] < 1 || v[0] > nv || v[1] > nv || v[2] > nv) { first_bad[c] = it.line; break; }
+                for (int k = 0; k < 3; k++) std::memcpy(&sc->tri[9 * f + 3 * (size_t)k], &verts[3 * (size_t)(v[k] - 1)], 12);
+                sc->tri_mat[f] = cur;
+                f++;
+            }
+        }
+    });
+    for (size_t c = 0; c < chunks; c++) {
+        if (first_bad[c] == UINT32_MAX) continue;
+        char buf[256];
+        line_cstr(data, lines[first_bad[c]], buf);
+        rt::set_error(std::string(obj_path) + ": unsupported face line: " + buf);
+        delete sc;
+        return RT_ERR_IO;
     }
 
     if (lights_path) {

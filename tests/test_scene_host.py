@@ -166,3 +166,62 @@ def test_bmp_writer_is_byte_identical_to_the_reference_writer(rt, tmp_path):
     top_down = rows_bottom_up[::-1].copy()
     rt.write_bmp(tmp_path / "o.bmp", top_down)
     assert (tmp_path / "o.bmp").read_bytes() == ref
+
+
+def _load_both(rt, d, monkeypatch, chunks):
+    monkeypatch.setenv("RT_LOADER_SERIAL", "1")
+    a = rt.Scene.load_dir(d).arrays()
+    monkeypatch.delenv("RT_LOADER_SERIAL")
+    monkeypatch.setenv("RT_LOADER_CHUNKS", str(chunks))
+    b = rt.Scene.load_dir(d).arrays()
+    monkeypatch.delenv("RT_LOADER_CHUNKS")
+    return a, b
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 64])
+def test_parallel_loader_equals_the_line_by_line_loader(rt, tmp_path, monkeypatch, chunks):
+    """The memory-speed loader (whole-file read, line index, chunks parsed on threads) against the sscanf-per-line one, on a
+    file built to sit on the rules: faces before their vertices, usemtl changes at chunk borders, CRLF, exponents, missing
+    coordinates, lines longer than the reference's 256-byte fgets buffer, unknown material names."""
+    rng = np.random.default_rng(5)
+    n_v = 400
+    lines = ["# header\r\n", "mtllib x.mtl\n", "f 1 2 3\n"]  # a face before any vertex
+    for i in range(n_v):
+        x, y, z = rng.normal(size=3)
+        style = i % 5
+        if style == 0: lines.append(f"v {x:.6f} {y:.6f} {z:.6f}\n")
+        elif style == 1: lines.append(f"v {x:.9e}  {y:.3E}\t{z:+.5f}\r\n")
+        elif style == 2: lines.append(f"v {x:.4f} {y:.4f}\n")                       # z missing -> 0
+        elif style == 3: lines.append(f"v   {x:.7f} {y:.7f} {z:.7f} 1.0 # w\n")
+        else: lines.append("v " + " " * 260 + f"{x:.6f} {y:.6f} {z:.6f}\n")        # > 255 characters: split by fgets
+        if i % 7 == 0: lines.append(f"vn {x:.3f} {y:.3f} {z:.3f}\n")
+    names = ["red", "late", "nosuch", "red2"]
+    for i in range(900):
+        if i % 11 == 0: lines.append(f"usemtl {names[(i // 11) % 4]}\n")
+        a, b, c = rng.integers(1, n_v + 1, size=3)
+        lines.append(f"f {a} {b} {c}\n" if i % 3 else f"f  {a}\t{b} {c} \r\n")
+        if i % 50 == 0: lines.append("s off\n")
+    (tmp_path / "triangles.obj").write_text("".join(lines), newline="")
+    (tmp_path / "triangles.mtl").write_text("newmtl red\nKd 0.8 0.1 0.1\nKs 0.5 0.5 0.5\nKr 0.2 0.2 0.2\n\nnewmtl late\nKd 0.1 0.2 0.3\n\nnewmtl red2\nKs 1 1 1\n")
+    (tmp_path / "lights.obj").write_text("0 -8 3 50 50 50\n")
+    a, b = _load_both(rt, tmp_path, monkeypatch, chunks)
+    assert a["tri"].shape == (901, 9)
+    for k in a:
+        assert np.array_equal(a[k].view(np.uint8), b[k].view(np.uint8)), k
+
+
+def test_parallel_loader_reports_the_first_bad_face(rt, tmp_path, monkeypatch):
+    body = "".join(f"v {i} 0 0\n" for i in range(50)) + "".join(f"f {1 + i % 48} {2 + i % 48} {3 + i % 48}\n" for i in range(300))
+    body = body.replace("f 5 6 7\n", "f 5 6 99\n", 1) + "f 1/1 2/2 3/3\n"
+    (tmp_path / "triangles.obj").write_text(body)
+    (tmp_path / "triangles.mtl").write_text("")
+    (tmp_path / "lights.obj").write_text("")
+    msgs = []
+    for env in ({"RT_LOADER_SERIAL": "1"}, {"RT_LOADER_CHUNKS": "16"}):
+        for k, v in env.items(): monkeypatch.setenv(k, v)
+        with pytest.raises(rt.RtError) as e:
+            rt.Scene.load_dir(tmp_path)
+        assert e.value.code == rt.RT_ERR_IO
+        msgs.append(str(e.value))
+        for k in env: monkeypatch.delenv(k)
+    assert msgs[0] == msgs[1] and "f 5 6 99" in msgs[0]
