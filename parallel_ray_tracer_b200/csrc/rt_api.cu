@@ -349,6 +349,16 @@ static int create_common(const rt::FlatScene& flat, rt::DeviceFlat* pre, const i
             c->copy_stream = D.aux;
             for (int s = 0; s < RT_FRAME_SLOTS; s++) CKC(cudaEventCreateWithFlags(&c->slots[s].copy_done, cudaEventDisableTiming));
         }
+        if (i > 0) { // NVLink / NVSwitch peer mapping towards the frame owner (also makes the fan-out a direct peer copy)
+            int can = 0;
+            CKC(cudaDeviceCanAccessPeer(&can, D.id, c->devs[0].id));
+            if (can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(c->devs[0].id, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+                CKC(e);
+                D.peer_to_0 = true;
+            }
+        }
         // One host->device upload (device 0), then fan-out device 0 -> device i over NVLink / NVSwitch: the other devices
         // do not pull the scene through PCIe again (the reference uploads once to its single device, gpu/src/gpu.cu:143-175).
         auto put = [&](auto** dst, const void* host, auto* const* src0, size_t bytes) -> cudaError_t {
@@ -373,17 +383,12 @@ static int create_common(const rt::FlatScene& flat, rt::DeviceFlat* pre, const i
         CKC(put(&D.lights, flat.lights.data(), &Z.lights, flat.lights.size() * 4));
         CKC(cudaMalloc((void**)&D.ctrl, 8 * RT_CTRL_WORDS * RT_FRAME_SLOTS));
         CKC(cudaMallocHost((void**)&D.ctrl_host, 64 * RT_FRAME_SLOTS));
-        CKC(cudaStreamSynchronize(D.stream));
-        if (i > 0) { // NVLink / NVSwitch peer mapping towards the frame owner
-            int can = 0;
-            CKC(cudaDeviceCanAccessPeer(&can, D.id, c->devs[0].id));
-            if (can) {
-                cudaError_t e = cudaDeviceEnablePeerAccess(c->devs[0].id, 0);
-                if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
-                CKC(e);
-                D.peer_to_0 = true;
-            }
-        }
+        if (i == 0) CKC(cudaStreamSynchronize(D.stream)); // the fan-out below reads device 0's arrays
+    }
+    // the fan-out copies of all devices run concurrently (NVSwitch: full bandwidth from device 0 to every peer)
+    for (int i = 1; i < ndev; i++) {
+        CKC(cudaSetDevice(c->devs[i].id));
+        CKC(cudaStreamSynchronize(c->devs[i].stream));
     }
 #undef CKC
     *out = c;
