@@ -122,3 +122,31 @@ def test_multi_device_sequence(rt, gpu_scenes):
         ctx1.render_frame(rt.default_params(width=w, height=h, cam=cs[k]))
         assert np.array_equal(ctx1.load_from_gpu()["bgra"].reshape(-1), bufs[k % 2].array)
     ctxn.close()
+
+
+def test_sequence_error_paths(rt, gpu_scenes):
+    _, ctx = gpu_scenes["soup2k"]
+    fresh = rt.Context(gpu_scenes["soup2k"][0], [0])
+    buf = rt.PinnedBuffer(64 * 36 * 4)
+    with pytest.raises(rt.RtError) as e:
+        fresh.download_async(0, buf.ptr)          # nothing rendered on the slot
+    assert e.value.code == rt.RT_ERR_STATE
+    with pytest.raises(rt.RtError) as e:
+        fresh.frame_wait(1)
+    assert e.value.code == rt.RT_ERR_STATE
+    with pytest.raises(rt.RtError) as e:
+        fresh.frame_wait(5)
+    assert e.value.code == rt.RT_ERR_INVALID
+    fresh.render_frame_async(rt.default_params(width=64, height=36, frame_slot=0))
+    fresh.download_async(0, buf.ptr)
+    t1 = fresh.frame_wait(0)
+    t2 = fresh.frame_wait(0)                      # waiting twice returns the same timing
+    assert (t1.rays_closest, t1.kernel_ms[0]) == (t2.rays_closest, t2.kernel_ms[0]) and t1.rays_closest == 64 * 36
+    ctx.render_frame(rt.default_params(width=64, height=36))
+    assert np.array_equal(buf.array.reshape(36, 64, 4), ctx.load_from_gpu()["bgra"])
+    # bottom-up rows are refused where tiles are packed
+    fresh.render_frame(rt.default_params(width=64, height=36, frame_flags=rt.RT_FRAME_BOTTOM_UP, part_index=0, part_count=2))
+    with pytest.raises(rt.RtError) as e:
+        fresh.packed_tiles()
+    assert e.value.code == rt.RT_ERR_STATE
+    fresh.close(); buf.close()
