@@ -257,9 +257,9 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
         return tm, tm.kernel_ms[0] + g
 
     # ---- warm-up, then EXACTLY K timed steps ----
+    sampler = ClockSampler(local) if rank == 0 else None   # started before the warm-up: nvidia-smi needs ~0.1 s to deliver its first sample
     for _ in range(max(args.warmup, 3)):
         step(True)
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier(); torch.cuda.synchronize()
     dev_ms, kern_ms, launches = [], [], 0
     t_wall0 = time.perf_counter()
