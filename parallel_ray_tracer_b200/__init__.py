@@ -45,7 +45,7 @@ EXPORTS = [
     "rt_part_tile_count", "rt_packed_tiles", "rt_unpack_tiles", "rt_frame_ipc_export", "rt_frame_ipc_import",
     "rt_frame_device_ptr", "rt_write_bmp", "rt_abi_version", "rt_device_count", "rt_debug_warp_trace",
     "rt_render_async", "rt_download_async", "rt_frame_wait", "rt_host_alloc", "rt_host_free",
-    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order", "rt_scene_build_bvh_gpu", "rt_debug_gather_bandwidth", "rt_create_gpu",
+    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order", "rt_scene_build_bvh_gpu", "rt_debug_gather_bandwidth", "rt_create_gpu", "rt_debug_flatten_host",
 ]
 
 
@@ -126,6 +126,7 @@ def lib() -> C.CDLL:
     L.rt_scene_free.argtypes = [vp]; L.rt_scene_free.restype = None
     L.rt_render_params_default.argtypes = [C.POINTER(rt_render_params)]; L.rt_render_params_default.restype = None
     L.rt_create.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(i32), i32, C.POINTER(vp)]
+    L.rt_debug_flatten_host.argtypes = [C.POINTER(rt_scene_desc), i32, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(i32)]
     L.rt_create_gpu.argtypes = [vp, i32, C.POINTER(i32), i32, i32, C.POINTER(vp), C.POINTER(rt_bvh_gpu_stats)]
     L.rt_render.argtypes = [vp, C.POINTER(rt_render_params), C.POINTER(rt_timing)]
     L.rt_download.argtypes = [vp, vp, vp, vp, vp]
@@ -236,6 +237,20 @@ class Scene:
         st = rt_bvh_gpu_stats()
         _check(lib().rt_scene_build_bvh_gpu(self._h, heuristic, device, C.byref(st)))
         return st
+
+    def flatten_host(self) -> dict:
+        """The staging arrays rt_create would upload (host only, rt_debug_flatten_host)."""
+        d = self.view()
+        out, meta = {}, (C.c_int * 4)()
+        for which, (name, dt) in enumerate([("nodes", np.float32), ("nodes4", np.float32), ("tris", np.float32), ("shade", np.float32),
+                                            ("leaf_cnt", np.int32), ("mats", np.float32), ("lights", np.float32)]):
+            n = C.c_size_t()
+            _check(lib().rt_debug_flatten_host(C.byref(d), which, None, 0, C.byref(n), meta))
+            a = np.empty(n.value // 4, dt)
+            _check(lib().rt_debug_flatten_host(C.byref(d), which, _ptr(a), a.nbytes, C.byref(n), meta))
+            out[name] = a
+        out["max_depth"], out["stack_need4"], out["n_lights"] = meta[0], meta[1], meta[2]
+        return out
 
     def view(self) -> rt_scene_desc:
         d = rt_scene_desc()

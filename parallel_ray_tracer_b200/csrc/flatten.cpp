@@ -295,3 +295,34 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
 }
 
 } // namespace rt
+
+// Host-only view of the staging arrays (no device needed): lets the CPU test tier check the layout rules of
+// device_layout.h and that the threaded passes do not depend on the thread count.
+extern "C" int rt_debug_flatten_host(const rt_scene_desc* desc, int which, void* out, size_t cap_bytes, size_t* bytes_out, int* meta4)
+{
+    if (!desc || !bytes_out) { rt::set_error("rt_debug_flatten_host: null argument"); return RT_ERR_INVALID; }
+    rt::FlatScene flat;
+    std::string err;
+    const int rc = rt::flatten_scene(*desc, flat, err);
+    if (rc) { rt::set_error("rt_debug_flatten_host: " + err); return rc; }
+    const void* src = nullptr;
+    size_t n = 0;
+    switch (which) {
+    case 0: src = flat.nodes.data(); n = flat.nodes.size() * 4; break;
+    case 1: src = flat.nodes4.data(); n = flat.nodes4.size() * 4; break;
+    case 2: src = flat.tris.data(); n = flat.tris.size() * 4; break;
+    case 3: src = flat.shade.data(); n = flat.shade.size() * 4; break;
+    case 4: src = flat.leaf_cnt.data(); n = flat.leaf_cnt.size() * 4; break;
+    case 5: src = flat.mats.data(); n = flat.mats.size() * 4; break;
+    case 6: src = flat.lights.data(); n = flat.lights.size() * 4; break;
+    default: rt::set_error("rt_debug_flatten_host: bad array selector"); return RT_ERR_INVALID;
+    }
+    *bytes_out = n;
+    if (meta4) { meta4[0] = flat.max_depth; meta4[1] = flat.stack_need4; meta4[2] = (int)flat.n_lights; meta4[3] = 0; }
+    if (out) {
+        if (cap_bytes < n) { rt::set_error("rt_debug_flatten_host: buffer too small"); return RT_ERR_INVALID; }
+        if (n) std::memcpy(out, src, n);
+    }
+    return RT_OK;
+}
+

@@ -1,0 +1,206 @@
+"""The HBM layout (csrc/device_layout.h) as produced by the host flatten (csrc/flatten.cpp), checked on the CPU through
+rt_debug_flatten_host: structural rules, the 4-wide collapse against the 2-wide records, independence from the thread count,
+and — by walking the flattened records with numpy — the same first hits as the oracle's bvh_traverse."""
+import numpy as np
+import pytest
+
+from conftest import GOLD, SCENES
+
+REF_NONE = -(1 << 31)
+
+
+def flat_of(rt, scene, heuristic=6):
+    sc = rt.Scene.load_rtsc(GOLD / "scenes" / f"{scene}.rtsc").build_bvh(heuristic)
+    f, a = sc.flatten_host(), sc.arrays()
+    sc.close()
+    return f, a
+
+
+def refs2(f):
+    return f["nodes"].reshape(-1, 16)[:, 12:14].view(np.int32)
+
+
+def leaf_range(f, ref):
+    v = ~int(ref)
+    first, cnt = v >> 4, v & 15
+    if cnt == 15:
+        cnt = int(f["leaf_cnt"][first])
+    return first, cnt
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_layout_rules(rt, scene):
+    f, a = flat_of(rt, scene)
+    n = len(a["tri"])
+    nodes = f["nodes"].reshape(-1, 16)
+    r2 = refs2(f)
+    n_inner = len(nodes)
+    # every triangle slot is covered by exactly one leaf reference, every inner record is referenced exactly once (record 0 = root)
+    seen_tri = np.zeros(n, int)
+    seen_node = np.zeros(n_inner, int)
+    for ref in r2.reshape(-1):
+        if ref == REF_NONE:
+            continue
+        if ref >= 0:
+            seen_node[ref] += 1
+        else:
+            first, cnt = leaf_range(f, ref)
+            seen_tri[first:first + cnt] += 1
+    assert (seen_tri == 1).all() and (seen_node[1:] == 1).all() and seen_node[0] == 0
+    # triangle records: v0, e1, e2, n = e1 x e2 of the triangle tri_idx[j], original index in the fourth quad
+    t = f["tris"].reshape(n, 16)
+    orig = t[:, 12].view(np.int32)
+    assert np.array_equal(orig, a["tri_idx"])
+    c = a["tri"][orig]
+    assert np.array_equal(t[:, 0:3], c[:, 0:3])
+    assert np.array_equal(t[:, 3:6], c[:, 3:6] - c[:, 0:3]) and np.array_equal(t[:, 6:9], c[:, 6:9] - c[:, 0:3])
+    e1, e2 = t[:, 3:6].astype(np.float32), t[:, 6:9].astype(np.float32)
+    nn = np.stack([e1[:, 1] * e2[:, 2] - e1[:, 2] * e2[:, 1], e1[:, 2] * e2[:, 0] - e1[:, 0] * e2[:, 2], e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]], 1)
+    assert np.array_equal(t[:, 9:12], nn.astype(np.float32))
+    assert (t[:, 13:16] == 0).all()
+    # child boxes contain the triangles below them (leaves) and the boxes below them (inner children)
+    for k in range(0, n_inner, max(1, n_inner // 300)):
+        for w in (0, 1):
+            ref = r2[k, w]
+            mn = nodes[k, [0, 1, 2]] if w == 0 else nodes[k, [6, 7, 8]]
+            mx = nodes[k, [3, 4, 5]] if w == 0 else nodes[k, [9, 10, 11]]
+            if ref == REF_NONE:
+                assert np.isinf(mn).all() and np.isinf(mx).all()
+            elif ref >= 0:
+                sub = nodes[ref]
+                lo = np.minimum(sub[[0, 1, 2]], sub[[6, 7, 8]]); hi = np.maximum(sub[[3, 4, 5]], sub[[9, 10, 11]])
+                fin = np.isfinite(lo) & np.isfinite(hi)
+                assert (lo[fin] >= mn[fin]).all() and (hi[fin] <= mx[fin]).all()
+            else:
+                first, cnt = leaf_range(f, ref)
+                v = a["tri"][a["tri_idx"][first:first + cnt]].reshape(-1, 3)
+                assert (v.min(0) >= mn).all() and (v.max(0) <= mx).all()
+    assert f["max_depth"] <= 32 and f["stack_need4"] >= 3
+
+
+@pytest.mark.parametrize("scene", SCENES)
+def test_four_wide_collapse_matches_the_two_wide_records(rt, scene):
+    f, _ = flat_of(rt, scene)
+    nodes, r2 = f["nodes"].reshape(-1, 16), refs2(f)
+    n4 = f["nodes4"].reshape(-1, 32)
+    r4 = n4[:, 24:28].view(np.int32)
+
+    def box2(k, w):
+        return (nodes[k, [0, 1, 2]], nodes[k, [3, 4, 5]]) if w == 0 else (nodes[k, [6, 7, 8]], nodes[k, [9, 10, 11]])
+
+    # walk both trees together from the roots: a 4-wide node holds the grandchildren of a 2-wide node, a leaf child as it is
+    stack, visited = [(0, 0)], 0
+    while stack:
+        k2, k4 = stack.pop()
+        visited += 1
+        kids = []
+        for w in (0, 1):
+            ref = r2[k2, w]
+            if ref >= 0:
+                kids += [(r2[ref, 0], box2(ref, 0)), (r2[ref, 1], box2(ref, 1))]
+            else:
+                kids.append((ref, box2(k2, w)))
+        slot = 0
+        for i, (ref, (mn, mx)) in enumerate(kids):
+            if ref == REF_NONE:
+                assert r4[k4, i] == REF_NONE
+                continue
+            assert np.array_equal(n4[k4, [0 + i, 4 + i, 8 + i]], mn) and np.array_equal(n4[k4, [12 + i, 16 + i, 20 + i]], mx)
+            if ref >= 0:
+                stack.append((int(ref), int(r4[k4, i])))
+            else:
+                assert r4[k4, i] == ref
+            slot += 1
+        for i in range(len(kids), 4):
+            assert r4[k4, i] == REF_NONE and np.isinf(n4[k4, i])
+    assert visited == len(n4)
+
+
+def test_flatten_does_not_depend_on_the_thread_count(rt, monkeypatch):
+    sc = rt.Scene.load_rtsc(GOLD / "scenes" / "car_boxed.rtsc")
+    big = sc.instance_grid(2, 2, 1, (11.5, 6.5, 3.0))   # 184 K triangles: enough for several chunks
+    sc.close()
+    big.build_bvh(6)
+    # (the thread count is read once per process: compare a child process pinned to one thread with this one)
+    import hashlib, subprocess, sys, textwrap
+    def digest(f):
+        h = hashlib.sha256()
+        for k in ("nodes", "nodes4", "tris", "shade", "leaf_cnt", "mats", "lights"):
+            h.update(f[k].tobytes())
+        return h.hexdigest() + f":{f['max_depth']}:{f['stack_need4']}"
+    mine = digest(big.flatten_host())
+    big.close()
+    code = textwrap.dedent(f"""
+        import sys, hashlib; sys.path.insert(0, {str(GOLD.parent.parent)!r})
+        import parallel_ray_tracer_b200 as rt
+        sc = rt.Scene.load_rtsc({str(GOLD / 'scenes' / 'car_boxed.rtsc')!r}); big = sc.instance_grid(2, 2, 1, (11.5, 6.5, 3.0)); big.build_bvh(6)
+        f = big.flatten_host(); h = hashlib.sha256()
+        for k in ("nodes", "nodes4", "tris", "shade", "leaf_cnt", "mats", "lights"): h.update(f[k].tobytes())
+        print(h.hexdigest() + f":{{f['max_depth']}}:{{f['stack_need4']}}")
+    """)
+    import os
+    env = dict(os.environ, RT_FLATTEN_THREADS="1", RT_BVH_THREADS="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert r.stdout.strip() == mine
+
+
+@pytest.mark.parametrize("scene", ["soup2k", "car_only"])
+def test_walking_the_flattened_records_finds_the_oracle_hits(rt, oracle_scenes, scene):
+    """bvh_traverse (cpu/src/bvh.c:317-358) restated over the 64-byte records with plain numpy floats: first-hit triangle and t of
+    a few hundred primary rays must be the oracle's."""
+    f, a = flat_of(rt, scene)
+    nodes, r2 = f["nodes"].reshape(-1, 16).astype(np.float32), refs2(f)
+    tris = f["tris"].reshape(-1, 16)
+    w, h = 48, 27
+    ref = oracle_scenes[scene].render(w, h)
+    import oracle as O
+    basis = O.Oracle().camera_basis(O.DEFAULT_CAM_POS, O.DEFAULT_CAM_ROT, O.DEFAULT_FOV, w, h)
+    pos, ul, incx, incy = (np.asarray(basis[k], np.float32) for k in range(4))  # rows: pos, upper-left corner, inc_x, inc_y
+    F = np.float32
+    EPS = F(1e-3)
+
+    def box(o, d, mn, mx):
+        with np.errstate(all="ignore"):
+            t1, t2 = (mn - o) / d, (mx - o) / d
+        tmin = max(max(min(t1[0], t2[0]), min(t1[1], t2[1])), min(t1[2], t2[2]))
+        tmax = min(min(max(t1[0], t2[0]), max(t1[1], t2[1])), max(t1[2], t2[2]))
+        return tmin if (tmax >= tmin and tmax > 0) else F(np.inf)
+
+    def tri(o, d, j):
+        v0, e1, e2, n = tris[j, 0:3], tris[j, 3:6], tris[j, 6:9], tris[j, 9:12]
+        det = -F(d[0] * n[0] + d[1] * n[1] + d[2] * n[2])
+        if abs(det) < EPS:
+            return F(np.inf)
+        ao = o - v0
+        dao = np.array([ao[1] * d[2] - ao[2] * d[1], ao[2] * d[0] - ao[0] * d[2], ao[0] * d[1] - ao[1] * d[0]], F)
+        u = F(e2[0] * dao[0] + e2[1] * dao[1] + e2[2] * dao[2]) / det
+        v = -F(e1[0] * dao[0] + e1[1] * dao[1] + e1[2] * dao[2]) / det
+        t = F(ao[0] * n[0] + ao[1] * n[1] + ao[2] * n[2]) / det
+        return t if (t > EPS and u >= 0 and v >= 0 and u + v <= 1) else F(np.inf)
+
+    bad = 0
+    for y in range(0, h, 3):
+        for x in range(0, w, 2):
+            d = ((ul - pos) + incx * F(x)) + incy * F(y)
+            best_t, best = F(np.inf), -1
+            stack = [0]
+            while stack:
+                r = stack.pop()
+                if r < 0:
+                    first, cnt = leaf_range(f, r)
+                    for j in range(first, first + cnt):
+                        t = tri(pos, d, j)
+                        if t < best_t:
+                            best_t, best = t, int(tris[j, 12].view(np.int32))
+                    continue
+                tl = box(pos, d, nodes[r, [0, 1, 2]], nodes[r, [3, 4, 5]])
+                tr = box(pos, d, nodes[r, [6, 7, 8]], nodes[r, [9, 10, 11]])
+                (tn, rn), (tf, rf) = ((tl, r2[r, 0]), (tr, r2[r, 1])) if not (tr < tl) else ((tr, r2[r, 1]), (tl, r2[r, 0]))
+                if tf < best_t and rf != REF_NONE: stack.append(int(rf))
+                if tn < best_t and rn != REF_NONE: stack.append(int(rn))
+            if best != ref["id"][y, x]:
+                bad += 1
+            elif best >= 0:
+                assert abs(best_t - ref["depth"][y, x]) <= 1e-5 * abs(ref["depth"][y, x])
+    assert bad == 0
