@@ -507,9 +507,16 @@ def cpu_baseline(wl_name: str, wl: dict) -> dict:
     if ref.available:
         r = ref.run(rtsc=scene_file(wl["scene"]), width=wl["width"], height=wl["height"], spp=wl["spp"], threads=cores, frames=3, warmup=1, aov=False)
         ms = statistics.median(r["frame_ms"])
-        return {"value": rays / ms / 1e3, "unit": METRIC, "cores": cores, "kind": "reference", "frame_ms": ms,
-                "sample": f"median of 3 full frames of {wl_name} (+1 warm-up), {cores} pthreads, oracle/_ref (unmodified reference "
-                          f"sources, -O3 -ffast-math -flto, {ref.isa}), heuristic-6 tree"}
+        out = {"value": rays / ms / 1e3, "unit": METRIC, "cores": cores, "kind": "reference", "frame_ms": ms,
+               "sample": f"median of 3 full frames of {wl_name} (+1 warm-up), {cores} pthreads, oracle/_ref (unmodified reference "
+                         f"sources, -O3 -ffast-math -flto, {ref.isa}), heuristic-6 tree"}
+        # the reference CPU program's own default tree (BVH_HEURISTIC 3, cpu/include/options.h:34): same image, slower walk
+        ref3 = O.RefCpu(3)
+        if ref3.available:
+            r3 = ref3.run(rtsc=scene_file(wl["scene"]), width=wl["width"], height=wl["height"], spp=wl["spp"], threads=cores, frames=2, warmup=1, aov=False)
+            ms3 = statistics.median(r3["frame_ms"])
+            out["heuristic3_tree"] = {"value": rays / ms3 / 1e3, "frame_ms": ms3, "note": "rays counted on the heuristic-6 tree; the image is the same"}
+        return out
     s = O.Oracle().scene(O.load_rtsc(scene_file(wl["scene"])))
     s.build_bvh(6 | 0x100)
     t = time.perf_counter(); s.render(wl["width"], wl["height"], spp=wl["spp"], threads=cores); ms = (time.perf_counter() - t) * 1e3
