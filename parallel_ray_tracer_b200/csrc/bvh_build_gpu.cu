@@ -475,18 +475,50 @@ __global__ void __launch_bounds__(kSubWarps * 32) subtree_kernel(int n_sub, cons
                 }
             }
             __syncwarp();
-            // ---- candidates: lane a evaluates axis a; the first strictly smaller cost in axis-major order wins ----
-            float best = FLT_MAX, my_pos = 0.f;
-            int my_axis = 0;
-            if (lane < 3)
-                choose_axis(lane, parent.min, parent.max, refbin, [&](int ax, int b) { return cnt[ax * kNB + b]; },
-                            [&](int ax, int b, float* m, float* x) { for (int a = 0; a < 3; a++) { m[a] = bmn[3 * (ax * kNB + b) + a]; x[a] = bmx[3 * (ax * kNB + b) + a]; } },
-                            best, my_axis, my_pos);
+            // ---- candidates (bvh.c:138-177): lane i evaluates plane i of one axis at a time.  Prefix / suffix unions of the
+            // bins by warp scans (min / max / integer sums: exact in any order); the first strictly smaller cost in
+            // axis-major, plane-ascending order wins = lexicographic minimum of (cost, plane) among the costs < FLT_MAX ----
             int splitAxis = 0;
-            float splitPos = 0.f, run = FLT_MAX;
-            for (int a = 0; a < 3; a++) {
-                const float ba = __shfl_sync(FULL, best, a), pa = __shfl_sync(FULL, my_pos, a);
-                if (ba < run) { run = ba; splitAxis = a; splitPos = pa; }
+            float splitPos = 0.f, best = FLT_MAX;
+            for (int axis = 0; axis < 3; axis++) {
+                const int bi = axis * kNB + lane;
+                float pm[3], px[3], sm[3], sx[3];
+                int pc = cnt[bi], sc_ = pc;
+                for (int a = 0; a < 3; a++) { pm[a] = sm[a] = bmn[3 * bi + a]; px[a] = sx[a] = bmx[3 * bi + a]; }
+                for (int o = 1; o < 32; o <<= 1) { // inclusive prefix over bins 0..lane, inclusive suffix over bins lane..31
+                    const int pcu = __shfl_up_sync(FULL, pc, o), scd = __shfl_down_sync(FULL, sc_, o);
+                    float pmu[3], pxu[3], smd[3], sxd[3];
+                    for (int a = 0; a < 3; a++) {
+                        pmu[a] = __shfl_up_sync(FULL, pm[a], o); pxu[a] = __shfl_up_sync(FULL, px[a], o);
+                        smd[a] = __shfl_down_sync(FULL, sm[a], o); sxd[a] = __shfl_down_sync(FULL, sx[a], o);
+                    }
+                    if (lane >= o) { pc += pcu; for (int a = 0; a < 3; a++) { pm[a] = fmn(pm[a], pmu[a]); px[a] = fmx(px[a], pxu[a]); } }
+                    if (lane + o < 32) { sc_ += scd; for (int a = 0; a < 3; a++) { sm[a] = fmn(sm[a], smd[a]); sx[a] = fmx(sx[a], sxd[a]); } }
+                }
+                // R_i = bins i+1 .. 32: the suffix of lane i+1 (none for lane 31) joined with bin 32
+                const int b32 = axis * kNB + kBins;
+                int cr = __shfl_down_sync(FULL, sc_, 1);
+                float rm[3], rx[3];
+                for (int a = 0; a < 3; a++) { rm[a] = __shfl_down_sync(FULL, sm[a], 1); rx[a] = __shfl_down_sync(FULL, sx[a], 1); }
+                if (lane == 31) { cr = 0; for (int a = 0; a < 3; a++) { rm[a] = INFINITY; rx[a] = -INFINITY; } }
+                cr += cnt[b32];
+                for (int a = 0; a < 3; a++) { rm[a] = fmn(rm[a], bmn[3 * b32 + a]); rx[a] = fmx(rx[a], bmx[3 * b32 + a]); }
+                float al_mn[3], al_mx[3], ar_mn[3], ar_mx[3]; // candidate boxes start at min = FLT_MAX, max = FLT_MIN (bvh.c:149-150)
+                for (int a = 0; a < 3; a++) {
+                    al_mn[a] = fmn(FLT_MAX, pm[a]); al_mx[a] = fmx(FLT_MIN, px[a]);
+                    ar_mn[a] = fmn(FLT_MAX, rm[a]); ar_mx[a] = fmx(FLT_MIN, rx[a]);
+                }
+                float score;
+                if (refbin) score = __fmaf_rn((float)pc, diag2(al_mn, al_mx, 1), (float)cr * diag2(ar_mn, ar_mx, 1));
+                else score = (float)pc * diag2(al_mn, al_mx, 0) + (float)cr * diag2(ar_mn, ar_mx, 0); // bvh.c:169
+                float key = score < FLT_MAX ? score : INFINITY; // NaN (0 * inf) and costs that can never win drop out
+                int idx = lane;
+                for (int o = 16; o; o >>= 1) {
+                    const float ko = __shfl_xor_sync(FULL, key, o);
+                    const int io = __shfl_xor_sync(FULL, idx, o);
+                    if (ko < key || (ko == key && io < idx)) { key = ko; idx = io; }
+                }
+                if (key < best) { best = key; splitAxis = axis; splitPos = split_plane(parent.min[axis], parent.max[axis] - parent.min[axis], idx, refbin); }
             }
             // ---- partition (bvh.c:244-259): lefts compacted in encounter order, rights by their chains ----
             float lb[6] = {1e10f, 1e10f, 1e10f, -1e10f, -1e10f, -1e10f}, rb[6] = {1e10f, 1e10f, 1e10f, -1e10f, -1e10f, -1e10f}; // bvh.c:104-108
