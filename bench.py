@@ -53,6 +53,12 @@ WORKLOADS = {
 METRIC = "Mrays/s"
 
 
+def config_of(wl_name: str, wl: dict) -> dict:
+    """The workload both arms are measured on — the SAME dict in both JSON lines (how each arm ran it goes under "run")."""
+    return {"workload": wl_name, **wl, "bounces": 4, "bvh": "heuristic 6 (reference GPU default, gpu/include/options.cuh:50)",
+            "camera": "reference default (cpu/src/main.c:105-106)"}
+
+
 def scene_file(name: str) -> Path:
     return ROOT / "tests" / "golden" / "scenes" / f"{name}.rtsc"
 
@@ -114,7 +120,7 @@ def reference_arm(args, wl_name: str, wl: dict) -> dict:
     cores = os.cpu_count() or 1
     base = {"impl": "reference", "metric": METRIC, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl_name, **wl, "bounces": 4, "bvh": "heuristic 6 (reference GPU default)", "camera": "reference default"}}
+            "config": config_of(wl_name, wl)}
     if not ref.available:
         base["unavailable"] = "oracle/_ref reference binary missing or not runnable on this host"
         return base
@@ -286,6 +292,8 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
     slot_params = []
     for slot in range(rt.RT_FRAME_SLOTS):
         slot_params.append(rt.default_params(**base, frame_slot=slot))
+    barrier_s = [0.0]   # host time inside dist.barrier() of the e2e loop (includes waiting for the slowest rank's kernel)
+
     def e2e_loop(steps):
         if gather == "nccl":
             for _ in range(steps):
@@ -310,7 +318,9 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
                 ctx.frame_wait(s)               # this rank's tiles of frame k are stored in rank 0's slot s
                 if rank == 0 and k >= 1:
                     ctx.frame_wait(1 - s)       # D2H of frame k-1 (ran during this render) is complete: slot 1-s is free again
+                tb = time.perf_counter()
                 barrier()                       # frame k on rank 0 is complete once every rank has stored its tiles
+                barrier_s[0] += time.perf_counter() - tb
                 if rank == 0:
                     ctx.download_async(s, pinned[s].data_ptr())
             if rank == 0:
@@ -319,10 +329,12 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
 
     e2e_loop(max(args.warmup, 4))   # untimed: second frame slot allocation, lazy IPC peer mapping, first NCCL barriers
     barrier(); torch.cuda.synchronize()
+    barrier_s[0] = 0.0
     t_e0 = time.perf_counter()
     e2e_loop(args.steps)
     torch.cuda.synchronize(); barrier()
     e2e_ms = (time.perf_counter() - t_e0) * 1e3 / args.steps
+    barrier_ms = barrier_s[0] * 1e3 / args.steps
     # unpipelined reference point: render, wait, copy, wait — one frame at a time
     barrier(); torch.cuda.synchronize()
     t_s0 = time.perf_counter()
@@ -360,6 +372,37 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
         afr = (afr_ms,)
         ctx_full.close()
 
+    # ---- multi-GPU correctness: the assembled N-part frame must be byte-identical to the frame one
+    # GPU renders alone.  Every frame slot is poisoned first, so a stale frame cannot pass. ----
+    def frame_check(cx, scene, w, h, spp, slots, asm):
+        if world == 1:
+            return None
+        full = None
+        if rank == 0:
+            c1 = rt.Context(scene, [local])
+            c1.render_frame(rt.default_params(width=w, height=h, spp=spp))
+            full = c1.load_from_gpu()["bgra"].copy()
+            c1.close()
+        ok = True
+        for slot in slots:
+            kw = dict(width=w, height=h, spp=spp, part_index=rank, part_count=world, frame_slot=slot)
+            cx.render_frame(rt.default_params(**kw))          # makes `slot` the context's current frame
+            if rank == 0:
+                ptr, nbytes = cx.frame_device_ptr()
+                torch.as_tensor(CudaArray(ptr, nbytes), device=dev).fill_(0x5a)
+            torch.cuda.synchronize(); barrier()
+            cx.render_frame(rt.default_params(**kw))
+            if asm:
+                assemble()
+            torch.cuda.synchronize(); barrier()
+            if rank == 0:
+                ok = ok and bool(np.array_equal(cx.load_from_gpu()["bgra"], full))
+        tk = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(tk, op=dist.ReduceOp.MIN)
+        return bool(tk.item() > 0)
+
+    frame_ok = frame_check(ctx, sc, W, H, SPP, range(rt.RT_FRAME_SLOTS) if gather == "ipc" else [0], gather == "nccl")
+
     # ---- reductions over ranks ----
     def allmax(x):
         if world == 1: return x
@@ -369,9 +412,14 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
         if world == 1: return x
         t = torch.tensor([x], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.SUM); return t.item()
 
-    total_dev_ms = allmax(sum(dev_ms))
-    total_kern_ms = allmax(sum(kern_ms))
-    total_warm_ms = allmax(sum(warm))
+    def sum_of_step_max(v):
+        """A strong-scaled frame is complete when its SLOWEST rank is: max over ranks per step, then the sum over steps."""
+        if world == 1: return float(sum(v))
+        tv = torch.tensor(v, dtype=torch.float64, device=dev); dist.all_reduce(tv, op=dist.ReduceOp.MAX); return float(tv.sum().item())
+
+    total_dev_ms = sum_of_step_max(dev_ms)
+    total_kern_ms = sum_of_step_max(kern_ms)
+    total_warm_ms = sum_of_step_max(warm)
     wall_ms = allmax(wall_ms)
     e2e_ms = allmax(e2e_ms)
     e2e_sync_ms = allmax(e2e_sync_ms)
@@ -422,11 +470,14 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
                 tm2 = ctx2.render_frame(p2)
                 ms2.append(tm2.kernel_ms[0])
             torch.cuda.synchronize(); barrier()
-            tot2 = allmax(sum(ms2)); rays2 = int(allsum(tm2.rays_closest + tm2.rays_shadow))
+            tot2 = sum_of_step_max(ms2); rays2 = int(allsum(tm2.rays_closest + tm2.rays_shadow))
             tmw2 = ctx2.render_frame(rt.default_params(width=W2, height=H2, spp=wl2["spp"], part_index=rank, part_count=world,
                                                        aov_mask=rt.RT_AOV_WORK, mode=rt.RT_MODE_STRICT))
             inner2 = int(allsum(tmw2.inner_visits)); tris2 = int(allsum(tmw2.tri_tests))
-            also = {"workload": args.also, **wl2, "steps": k2, "ms_per_step": tot2 / k2, "value": rays2 / (tot2 / k2) / 1e3, "unit": METRIC,
+            ok_also = frame_check(ctx2, sc2, W2, H2, wl2["spp"], [0], False)
+            if frame_ok is not None:
+                frame_ok = bool(frame_ok and ok_also)
+            also = {"workload": args.also, **wl2, "frame_equals_1gpu": ok_also, "steps": k2, "ms_per_step": tot2 / k2, "value": rays2 / (tot2 / k2) / 1e3, "unit": METRIC,
                     "rays_per_frame": rays2, "note": "same timing rules as value (CUDA events, max over ranks, L2 flushed), fused peer stores"}
             if rank == 0:
                 ach2 = (64 * inner2 + 40 * tris2) / world / (tot2 / k2 * 1e-3) / 1e9
@@ -455,28 +506,35 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
         out = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic",
-               "config": {"workload": wl_name, **wl, "bounces": 4, "bvh": "heuristic 6, built on the host as the reference does",
-                          "camera": "reference default (cpu/src/main.c:105-106)", "mode": "RT_MODE_FAST",
-                          "partition": f"{world} x interleaved 16x8 tiles" if world > 1 else "single GPU",
-                          "gather": {"ipc": "fused peer stores over NVLink (CUDA IPC)", "nccl": "packed tiles + NCCL all-gather + unpack",
-                                     "none": "none"}[gather],
-                          "l2": "flushed between timed frames (512 MiB overwrite)",
-                          "scene_note": "car_only as shipped by the reference; substitutions for missing scenes in DESIGN.md"},
+               "config": config_of(wl_name, wl),
+               "run": {"mode": "RT_MODE_FAST", "bvh_built": "on the host as the reference does (csrc/bvh_build.cpp)",
+                       "partition": f"{world} x interleaved 16x8 tiles" if world > 1 else "single GPU",
+                       "gather": {"ipc": "fused peer stores over NVLink (CUDA IPC)", "nccl": "packed tiles + NCCL all-gather + unpack",
+                                  "none": "none"}[gather],
+                       "l2": "flushed between timed frames (512 MiB overwrite)",
+                       "scene_note": "car_only as shipped by the reference; substitutions for missing scenes in DESIGN.md"},
+               "frame_equals_1gpu": frame_ok,
                "clocks": clocks,
                "e2e": {"value": rays / e2e_ms / 1e3, "unit": METRIC, "ms_per_step": e2e_ms,
                        "h2d_bytes_per_step": C.sizeof(rt.rt_render_params) * world, "d2h_bytes_per_step": W * H * 4,
                        "pipeline": ("synchronous (NCCL gather)" if gather == "nccl" else
                                     "frame k+1 renders while frame k is copied device->host (2 frame slots, rt_render_async / rt_download_async)"),
+                       "barrier_ms_per_step": barrier_ms,
                        "value_unpipelined": rays / e2e_sync_ms / 1e3, "ms_per_step_unpipelined": e2e_sync_ms},
                "gpu_launches": launches,
                "rays_per_frame": rays, "primary_mrays_s": W * H * SPP / ms_per_step / 1e3,
                "value_l2_warm": rays / (total_warm_ms / args.steps) / 1e3,
                "wall_ms_per_step_incl_flush": wall_ms / args.steps, "kernel_ms_per_step": k_ms,
                "scene_upload_ms": create_ms,
-               "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                            "traffic": traffic, "peak_source": pk["source"],
-                            "note": "algorithmic bytes = 64 B x inner visits + 40 B x triangle tests per launch; the 4 MB scene is "
-                                    "L1/L2 resident, so this is not an HBM-bound kernel (frac > 1 is cache reuse); see roofline_fp32"},
+               "roofline": {"bound": "l1_gather", "achieved": ach, "peak": gather_peaks["l1_resident_64KB"], "unit": "GB/s",
+                            "frac": ach / gather_peaks["l1_resident_64KB"], "traffic": traffic,
+                            "peak_source": "measured live on this device by rt_debug_gather_bandwidth (random 64-byte records, working set in L1)",
+                            "frac_l2_gather": ach / gather_peaks["l2_resident_4MB"],
+                            "frac_hbm_stream": ach / pk["hbm_gbs"], "hbm_stream_peak": pk["hbm_gbs"], "hbm_peak_source": pk["source"],
+                            "note": "algorithmic bytes = 64 B x inner visits + 40 B x triangle tests per launch (SURVEY 8d, reference visit "
+                                    "order); the 4-5 MB scene is L1/L2 resident (DRAM traffic = `traffic`, ~0.1 % of the algorithmic bytes), so "
+                                    "the bound that applies is the L1 record-gather rate, not HBM; HBM only binds the 50 M-triangle scene "
+                                    "(profiles/r02_config5_*)"},
                "roofline_gather": {"unit": "GB/s", "achieved_algorithmic": ach, **{k: round(v, 1) for k, v in gather_peaks.items()},
                                    "frac_of_l1": ach / gather_peaks["l1_resident_64KB"], "frac_of_l2": ach / gather_peaks["l2_resident_4MB"],
                                    "note": "peaks measured live: random 64-byte-record gathers, one record per lane (the shape of a node fetch), working "
@@ -496,6 +554,29 @@ def gpu_arm(args, wl_name: str, wl: dict) -> dict:
         dist.destroy_process_group()
     ctx.close()
     return out
+
+
+def ref_gpu_baseline(wl: dict, rays: int) -> dict:
+    """The reference's own GPU program ("fuse", the only stage in its tree; staged + patched for gcc-hosted nvcc by
+    scripts/stage_ref_gpu.py into git-ignored baseline/_ref/gpu, -arch=sm_100) on this B200, at the best block shape of its
+    .bat sweeps (8x8, profiles/r01_reference_gpu_fuse_b200.jsonl), timed by ITS OWN protocol: CUDA events around the launch,
+    50 warm-up + 100 timed frames, median (gpu/src/main.cu:111-127).  It culls with round-to-nearest FP16 boxes
+    (gpu/src/gpu.cu:176-185): not parity-equivalent to the CPU renderer, a speed baseline only."""
+    import re
+    g = ROOT / "baseline" / "_ref" / "gpu"
+    exe = g / f"raytracer_{wl['scene']}_{wl['width']}x{wl['height']}"
+    if wl["spp"] != 1 or not exe.exists():
+        return {"unavailable": f"{exe.name} not staged (scripts/stage_ref_gpu.py builds it in the build container)"}
+    try:
+        r = subprocess.run([str(exe), "8", "8"], cwd=g, capture_output=True, text=True, timeout=600)
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{exe.name}: {e}"}
+    m = re.search(r"Frame time \(median\): ([0-9.]+) ms", r.stdout)
+    if r.returncode != 0 or not m:
+        return {"unavailable": f"{exe.name} failed: {(r.stderr or r.stdout)[-200:]}"}
+    ms = float(m.group(1))
+    return {"ms": ms, "mrays_s": rays / ms / 1e3, "block": "8x8", "protocol": "50 warm-up + 100 timed frames, CUDA events, median",
+            "note": "reference gpu/ kernel recompiled for sm_100; FP16 non-conservative culling; rays = this frame's oracle count"}
 
 
 def cpu_baseline(wl_name: str, wl: dict) -> dict:
@@ -536,6 +617,7 @@ def main():
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--refill", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference GPU program (baseline/_ref/gpu)")
     ap.add_argument("--also", default="car_boxed_4k", help="second workload reported under \"also\" ('' to skip)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -549,7 +631,19 @@ def main():
     if rank == 0:
         if args.gpus == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.workload, wl)
+        if args.gpus == 1 and not args.no_ref_gpu:
+            out["ref_gpu_baseline"] = ref_gpu_baseline(wl, out["rays_per_frame"])
+            if "ms" in out["ref_gpu_baseline"]:
+                out["ref_gpu_baseline"]["speedup_kernel"] = out["ref_gpu_baseline"]["ms"] / out["kernel_ms_per_step"]
+            if out.get("also"):
+                rg = ref_gpu_baseline(WORKLOADS[out["also"]["workload"]], out["also"]["rays_per_frame"])
+                if "ms" in rg:
+                    rg["speedup_kernel"] = rg["ms"] / out["also"]["ms_per_step"]
+                out["also"]["ref_gpu_baseline"] = rg
         print(json.dumps(out), flush=True)
+        if out.get("frame_equals_1gpu") is False:
+            print("bench.py: the assembled multi-GPU frame differs from the single-GPU frame", file=sys.stderr)
+            sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -269,8 +269,9 @@ int rt_debug_warp_trace(rt_ctx* ctx, int enable, unsigned long long* out, int ma
 /* Diagnostics: replace the first device's tile order (tile ids, ty * tiles_x + tx) for the current frame shape. */
 int rt_debug_set_tile_order(rt_ctx* ctx, const unsigned* tiles, int n);
 /* Diagnostics, host only (no device needed): the staging arrays rt_create would upload (csrc/device_layout.h).  which: 0 nodes
- * (64 B per inner node), 1 nodes4 (128 B), 2 tris (64 B per leaf-order slot), 3 shade (16 B), 4 leaf_cnt, 5 mats, 6 lights.
- * out may be NULL to query the size; meta4 receives {max_depth, stack_need4, n_lights, 0}. */
+ * (64 B per inner node), 1 nodes4 (128 B), 2 tris (64 B per leaf-order slot), 3 shade (16 B), 4 leaf_cnt, 5 mats, 6 lights, 7 nodes8
+ * (96 B per compressed 8-wide node, csrc/wide8.h).
+ * out may be NULL to query the size; meta4 receives {max_depth, stack_need4, n_lights, depth8}. */
 int rt_debug_flatten_host(const rt_scene_desc* desc, int which, void* out, size_t cap_bytes, size_t* bytes_out, int* meta4);
 /* Roofline microbenchmark: GB/s of random 64-byte-record gathers (the shape of a node fetch, one record per
  * lane) from a working set of ws_bytes on `device` — L1-, L2- or HBM-resident depending on the size. */

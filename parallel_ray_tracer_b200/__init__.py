@@ -243,13 +243,13 @@ class Scene:
         d = self.view()
         out, meta = {}, (C.c_int * 4)()
         for which, (name, dt) in enumerate([("nodes", np.float32), ("nodes4", np.float32), ("tris", np.float32), ("shade", np.float32),
-                                            ("leaf_cnt", np.int32), ("mats", np.float32), ("lights", np.float32)]):
+                                            ("leaf_cnt", np.int32), ("mats", np.float32), ("lights", np.float32), ("nodes8", np.uint32)]):
             n = C.c_size_t()
             _check(lib().rt_debug_flatten_host(C.byref(d), which, None, 0, C.byref(n), meta))
             a = np.empty(n.value // 4, dt)
             _check(lib().rt_debug_flatten_host(C.byref(d), which, _ptr(a), a.nbytes, C.byref(n), meta))
             out[name] = a
-        out["max_depth"], out["stack_need4"], out["n_lights"] = meta[0], meta[1], meta[2]
+        out["max_depth"], out["stack_need4"], out["n_lights"], out["depth8"] = meta[0], meta[1], meta[2], meta[3]
         return out
 
     def view(self) -> rt_scene_desc:

@@ -158,8 +158,7 @@ struct Builder {
             if (threads > 1 && len >= (1 << 18)) {
                 // min/max and integer counts are exact and order independent: chunked binning gives the same bins
                 std::vector<Bins> part((size_t)threads);
-                int used = 0;
-                parallel_for((size_t)len, 1 << 16, [&](int t, size_t lo, size_t hi) { bin_range(split, axis, first + (int)lo, first + (int)hi, part[t]); if (t + 1 > used) used = t + 1; });
+                parallel_for((size_t)len, 1 << 16, [&](int t, size_t lo, size_t hi) { bin_range(split, axis, first + (int)lo, first + (int)hi, part[t]); });
                 bins.clear();
                 const int t_used = (int)std::min<size_t>((size_t)threads, (size_t)len / (1 << 16));
                 for (int t = 0; t < std::max(t_used, 1); t++)
@@ -360,8 +359,12 @@ struct Builder {
     void run()
     {
         prepare();
-        if (heuristic == 6 && threads > 1 && n >= 200000) run_parallel();
-        else run_serial();
+        if (heuristic == 6 && threads > 1 && n >= 200000) {
+            run_parallel();
+            // The parallel build has no `bvh_len >= 2N` stop (cpu/src/bvh.c:80-83): a tree that reaches 2N nodes is one the
+            // reference would have cut short, so rebuild it with the serial builder, which carries the guard.
+            if (s.bvh.size() >= 2 * (size_t)n) run_serial();
+        } else run_serial();
     }
 };
 

@@ -38,6 +38,7 @@
 #include <vector>
 
 #include "gpu_tree.h"
+#include "staged_copy.h"
 #include "host_scene.h"
 
 namespace {
@@ -625,10 +626,12 @@ double now_ms()
 
 extern "C" int rt_scene_build_bvh_gpu(rt_scene* s, int heuristic, int device, rt_bvh_gpu_stats* stats)
 {
+    return rt::guarded("rt_scene_build_bvh_gpu", [&]() -> int {
     if (stats) std::memset(stats, 0, sizeof *stats);
     if (!s) { rt::set_error("rt_scene_build_bvh_gpu: null scene"); return RT_ERR_INVALID; }
     if ((heuristic & ~RT_BVH_REFBIN) != 6) { rt::set_error("rt_scene_build_bvh_gpu: only heuristic 6 is built on the GPU (use rt_scene_build_bvh for 0 / 1)"); return RT_ERR_INVALID; }
     return rt::gpu_build_bvh(*s, (heuristic & RT_BVH_REFBIN) ? 1 : 0, device, stats, nullptr);
+    });
 }
 
 int rt::gpu_build_bvh(rt_scene& scene, int refbin, int device, rt_bvh_gpu_stats* stats, GpuTree* keep)
@@ -668,7 +671,7 @@ int rt::gpu_build_bvh(rt_scene& scene, int refbin, int device, rt_bvh_gpu_stats*
     CKB(d_flags.alloc(sizeof(Flags)));
     mark("allocations");
     CKB(cudaMemsetAsync(d_flags.p, 0, sizeof(Flags), stream));
-    CKB(cudaMemcpyAsync(d_tri.p, s->tri.data(), n * 36, cudaMemcpyHostToDevice, stream));
+    CKB(rt::staged_h2d(d_tri.p, s->tri.data(), n * 36, stream)); // pinned ring, PCIe rate (staged_copy.h)
     mark("triangles host->device");
     prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_tri.as<float>(), d_info.as<float4>(), d_idx.as<int>(), (int)n, refbin);
     CKB(cudaGetLastError());
@@ -822,7 +825,7 @@ int rt::gpu_build_bvh(rt_scene& scene, int refbin, int device, rt_bvh_gpu_stats*
         st.total_ms = (float)(now_ms() - t_begin);
         if (stats) *stats = st;
         if (keep) keep->fell_back = true;
-        return rt::build_bvh(*s, 6, refbin ? rt::BVH_REFBIN : rt::BVH_IEEE, 0);
+        return rt::build_bvh(*s, 6, refbin ? rt::BVH_REFBIN : rt::BVH_IEEE, 1); // serial: it carries the reference's 2N guard
     }
     std::vector<int> task_of(top.size(), -1);
     for (int k = 0; k < n_sub; k++) task_of[(size_t)roots[(size_t)k].bfs] = k;
@@ -890,8 +893,9 @@ int rt::gpu_build_bvh(rt_scene& scene, int refbin, int device, rt_bvh_gpu_stats*
     } else {
         s->bvh.resize(total);
         s->tri_idx.resize(n);
-        CKB(cudaMemcpy(s->bvh.data(), d_out.p, total * sizeof(rt_bvh_node), cudaMemcpyDeviceToHost));
-        CKB(cudaMemcpy(s->tri_idx.data(), d_idx.p, n * 4, cudaMemcpyDeviceToHost));
+        CKB(cudaStreamSynchronize(stream));
+        CKB(rt::staged_d2h(s->bvh.data(), d_out.p, total * sizeof(rt_bvh_node), stream));
+        CKB(rt::staged_d2h(s->tri_idx.data(), d_idx.p, n * 4, stream));
     }
     mark("download");
     st.download_ms = (float)(now_ms() - t_down);

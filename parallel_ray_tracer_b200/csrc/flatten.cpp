@@ -14,6 +14,7 @@
 
 #include "flatten.h"
 #include "host_scene.h"
+#include "wide8.h"
 
 namespace rt {
 
@@ -291,6 +292,14 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
         }
         out.stack_need4 = (order4.empty() ? 0 : need4[0]) + 3; // + sentinel, postponed leaf, slack
     }
+    // ---- compressed 8-wide collapse (wide8.h): the fast build's default tree ----
+    {
+        Wide8Tree w8;
+        const int rc8 = build_wide8(d.bvh, nb, w8);
+        if (rc8) { err = "BVH child index out of range (8-wide collapse)"; return rc8; }
+        out.nodes8.assign(w8.words.begin(), w8.words.end());
+        out.depth8 = w8.depth;
+    }
     return RT_OK;
 }
 
@@ -315,10 +324,11 @@ extern "C" int rt_debug_flatten_host(const rt_scene_desc* desc, int which, void*
     case 4: src = flat.leaf_cnt.data(); n = flat.leaf_cnt.size() * 4; break;
     case 5: src = flat.mats.data(); n = flat.mats.size() * 4; break;
     case 6: src = flat.lights.data(); n = flat.lights.size() * 4; break;
+    case 7: src = flat.nodes8.data(); n = flat.nodes8.size() * 4; break;
     default: rt::set_error("rt_debug_flatten_host: bad array selector"); return RT_ERR_INVALID;
     }
     *bytes_out = n;
-    if (meta4) { meta4[0] = flat.max_depth; meta4[1] = flat.stack_need4; meta4[2] = (int)flat.n_lights; meta4[3] = 0; }
+    if (meta4) { meta4[0] = flat.max_depth; meta4[1] = flat.stack_need4; meta4[2] = (int)flat.n_lights; meta4[3] = flat.depth8; }
     if (out) {
         if (cap_bytes < n) { rt::set_error("rt_debug_flatten_host: buffer too small"); return RT_ERR_INVALID; }
         if (n) std::memcpy(out, src, n);

@@ -30,6 +30,8 @@ typedef std::vector<float, NoInitAlloc<float>> FloatBuf;
 struct FlatScene {
     FloatBuf             nodes;    // 16 floats (4 x float4) per inner node
     FloatBuf             nodes4;   // 32 floats (8 x float4) per 4-wide node (fast build)
+    std::vector<uint32_t, NoInitAlloc<uint32_t>> nodes8; // 24 words per compressed 8-wide node (fast build; wide8.h)
+    int depth8 = 0;                // levels of the 8-wide tree
     FloatBuf             tris;     // 16 floats (4 x float4) per leaf-order slot
     FloatBuf             shade;    // 4 floats per original triangle
     std::vector<float>   mats;     // 12 floats per material
@@ -42,7 +44,7 @@ struct FlatScene {
 
     size_t bytes() const
     {
-        return 4 * (nodes.size() + nodes4.size() + tris.size() + shade.size() + mats.size() + lights.size() + leaf_cnt.size());
+        return 4 * (nodes.size() + nodes4.size() + nodes8.size() + tris.size() + shade.size() + mats.size() + lights.size() + leaf_cnt.size());
     }
 };
 

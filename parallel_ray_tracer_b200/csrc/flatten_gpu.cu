@@ -16,6 +16,7 @@
 
 #include "device_layout.h"
 #include "gpu_tree.h"
+#include "staged_copy.h"
 
 namespace {
 
@@ -180,7 +181,7 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
     CKF(cudaMemset(flags.p, 0, sizeof(FlatFlags)));
     if (host_tri_mat) {
         CKF(mat.alloc((size_t)n * 4));
-        CKF(cudaMemcpy(mat.p, host_tri_mat, (size_t)n * 4, cudaMemcpyHostToDevice));
+        CKF(rt::staged_h2d(mat.p, host_tri_mat, (size_t)n * 4, 0));
     }
     const int B = 256;
     tris_kernel<<<(n + B - 1) / B, B>>>(n, t.tri, t.tri_idx, tris.as<float4>());

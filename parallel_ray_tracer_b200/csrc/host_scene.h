@@ -1,6 +1,8 @@
 // host_scene.h — host-side scene container behind the opaque rt_scene of include/rt_b200.h.
 #pragma once
 #include <cstdint>
+#include <exception>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -25,6 +27,15 @@ namespace rt {
 // thread-local error text for calls that have no context yet
 void set_error(const std::string& msg);
 const char* get_error();
+
+// No C++ exception may cross the C ABI: extern "C" entry points that allocate run their body through this.
+template <class F>
+inline int guarded(const char* who, F f)
+{
+    try { return f(); }
+    catch (const std::bad_alloc&) { set_error(std::string(who) + ": out of memory"); return RT_ERR_NOMEM; }
+    catch (const std::exception& e) { set_error(std::string(who) + ": " + e.what()); return RT_ERR_INVALID; }
+}
 
 // BVH build variants (bvh_build.cpp)
 enum BvhArith {

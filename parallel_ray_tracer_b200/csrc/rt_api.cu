@@ -19,6 +19,7 @@
 #include "gpu_tree.h"
 #include "host_scene.h"
 #include "render_launch.h"
+#include "staged_copy.h"
 
 namespace {
 
@@ -50,10 +51,6 @@ struct Dev {
     size_t bgra_px = 0;
     uchar4* packed = nullptr; // packed tiles (gather paths)
     size_t packed_px = 0;
-    float* rgb = nullptr;
-    int* tri_id = nullptr;
-    float* depth = nullptr;
-    size_t aov_px[3] = {0, 0, 0};
     bool peer_to_0 = false;
     unsigned long long* warp_trace = nullptr; // diagnostics (rt_debug_warp_trace)
     size_t warp_trace_cap = 0;
@@ -67,6 +64,12 @@ namespace {
 struct Slot {
     uchar4* bgra = nullptr;
     size_t bgra_px = 0;
+    // AOVs of the frame rendered on this slot (device 0, peer-stored by the other devices like the BGRA frame): one set per
+    // slot, so that a render queued on the other slot cannot overwrite what rt_download returns for this one
+    float* rgb = nullptr;
+    int* tri_id = nullptr;
+    float* depth = nullptr;
+    size_t aov_px[3] = {0, 0, 0};
     uchar4* ipc_frame = nullptr; // another process's frame (CUDA IPC): the peer-store target of this slot's renders
     int ipc_w = 0, ipc_h = 0;
     cudaEvent_t copy_done = nullptr;
@@ -99,9 +102,6 @@ struct rt_ctx {
     size_t gather_px = 0;
     size_t scene_bytes = 0;
     int max_depth = 0, stack_need4 = 0;
-    // rays per device of the last frame and the shape they belong to (scheduling default, see rt_render)
-    double rays_per_dev = 0;
-    int rays_w = 0, rays_h = 0, rays_spp = 0, rays_parts = 0;
     bool want_trace = false;
 };
 
@@ -131,7 +131,7 @@ cudaError_t upload(T** dst, const void* src, size_t bytes, cudaStream_t st)
     if (!bytes) { *dst = nullptr; return cudaSuccess; }
     cudaError_t e = cudaMalloc((void**)dst, bytes);
     if (e != cudaSuccess) return e;
-    return cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, st);
+    return rt::staged_h2d(*dst, src, bytes, st); // pageable staging vectors -> pinned ring -> device (staged_copy.h)
 }
 
 // ------------------------------------------------------------------ frame kernels
@@ -265,7 +265,7 @@ void free_dev(Dev& D)
     cudaSetDevice(D.id);
     cudaFree(D.nodes); cudaFree(D.nodes4); cudaFree(D.tris); cudaFree(D.shade); cudaFree(D.mats); cudaFree(D.lights);
     cudaFree(D.leaf_cnt); cudaFree(D.ctrl); cudaFree(D.tile_list); cudaFree(D.warp_trace);
-    cudaFree(D.bgra); cudaFree(D.packed); cudaFree(D.rgb); cudaFree(D.tri_id); cudaFree(D.depth);
+    cudaFree(D.bgra); cudaFree(D.packed);
     if (D.ctrl_host) cudaFreeHost(D.ctrl_host);
     for (int s = 0; s < RT_FRAME_SLOTS; s++) {
         if (D.ev0[s]) cudaEventDestroy(D.ev0[s]);
@@ -408,6 +408,7 @@ static int check_devices(const char* who, const int*& devices, int& ndev, const 
 
 int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** out)
 {
+    return rt::guarded("rt_create", [&]() -> int {
     if (!desc || !out) return fail(nullptr, RT_ERR_INVALID, "rt_create: null argument");
     *out = nullptr;
     const int dflt = 0;
@@ -418,12 +419,14 @@ int rt_create(const rt_scene_desc* desc, const int* devices, int ndev, rt_ctx** 
     rc = rt::flatten_scene(*desc, flat, err);
     if (rc) return fail(nullptr, rc, "rt_create: " + err);
     return create_common(flat, nullptr, devices, ndev, out);
+    });
 }
 
 // Triangles -> render-ready context without the tree visiting the host: heuristic-6 BVH built on devices[0]
 // (bvh_build_gpu.cu), flattened there (flatten_gpu.cu), fanned out to the other devices over NVLink.
 int rt_create_gpu(rt_scene* s, int heuristic, const int* devices, int ndev, int download_tree, rt_ctx** out, rt_bvh_gpu_stats* stats)
 {
+    return rt::guarded("rt_create_gpu", [&]() -> int {
     if (stats) std::memset(stats, 0, sizeof *stats);
     if (!s || !out) return fail(nullptr, RT_ERR_INVALID, "rt_create_gpu: null argument");
     *out = nullptr;
@@ -457,6 +460,7 @@ int rt_create_gpu(rt_scene* s, int heuristic, const int* devices, int ndev, int 
     rc = create_common(small, &df, devices, ndev, out);
     cudaFree(df.nodes); cudaFree(df.nodes4); cudaFree(df.tris); cudaFree(df.shade); cudaFree(df.leaf_cnt); // (null once adopted)
     return rc;
+    });
 }
 
 void rt_destroy(rt_ctx* c)
@@ -467,7 +471,7 @@ void rt_destroy(rt_ctx* c)
         cudaDeviceSynchronize();
         for (Slot& S : c->slots) {
             if (S.ipc_frame) cudaIpcCloseMemHandle(S.ipc_frame);
-            cudaFree(S.bgra);
+            cudaFree(S.bgra); cudaFree(S.rgb); cudaFree(S.tri_id); cudaFree(S.depth);
             if (S.copy_done) cudaEventDestroy(S.copy_done);
         }
         cudaFree(c->local_index); cudaFree(c->gather_buf);
@@ -503,6 +507,8 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
     if (nd > 1 && gather == RT_GATHER_PEER_COPY && (p->frame_flags & RT_FRAME_BOTTOM_UP))
         return fail(c, RT_ERR_INVALID, "rt_render: RT_FRAME_BOTTOM_UP is not available with RT_GATHER_PEER_COPY");
     if (S.ipc_frame && (S.ipc_w != w || S.ipc_h != h)) return fail(c, RT_ERR_STATE, "rt_render: imported frame has another size");
+    if (nd > 1 && gather == RT_GATHER_PEER_COPY && S.ipc_frame)
+        return fail(c, RT_ERR_INVALID, "rt_render: RT_GATHER_PEER_COPY cannot assemble into an imported (CUDA IPC) frame");
     if (nd > 1 && part_count > 1) return fail(c, RT_ERR_INVALID, "rt_render: use either several devices per context or part_count > 1");
 
     int rc = setup_tiles(c, w, h, p->part_index, part_count);
@@ -511,10 +517,20 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
     // frame storage on device 0 (+ local frames for PEER_COPY)
     Dev& D0 = c->devs[0];
     CK(c, cudaSetDevice(D0.id));
+    {   // Growing a buffer frees the old one: nothing queued on this slot may still touch it.  The slot has been waited on
+        // (render_pending is false), which covers every device's render kernel; a device->host copy may still be in flight.
+        const bool grow = (!S.ipc_frame && S.bgra_px < npx) || ((p->aov_mask & RT_AOV_RGB_F32) && S.aov_px[0] < 3 * npx) ||
+                          ((p->aov_mask & RT_AOV_TRI_ID) && S.aov_px[1] < npx) || ((p->aov_mask & RT_AOV_DEPTH) && S.aov_px[2] < npx);
+        if (grow) {
+            if (S.copy_pending) { CK(c, cudaEventSynchronize(S.copy_done)); S.copy_pending = false; }
+            for (Dev& D : c->devs) { CK(c, cudaSetDevice(D.id)); CK(c, cudaStreamSynchronize(D.stream)); }
+            CK(c, cudaSetDevice(D0.id));
+        }
+    }
     if (!S.ipc_frame && (rc = ensure(c, &S.bgra, &S.bgra_px, npx))) return rc; // an imported frame is the target: no local one
-    if (p->aov_mask & RT_AOV_RGB_F32) { if ((rc = ensure(c, &D0.rgb, &D0.aov_px[0], 3 * npx))) return rc; }
-    if (p->aov_mask & RT_AOV_TRI_ID) { if ((rc = ensure(c, &D0.tri_id, &D0.aov_px[1], npx))) return rc; }
-    if (p->aov_mask & RT_AOV_DEPTH) { if ((rc = ensure(c, &D0.depth, &D0.aov_px[2], npx))) return rc; }
+    if (p->aov_mask & RT_AOV_RGB_F32) { if ((rc = ensure(c, &S.rgb, &S.aov_px[0], 3 * npx))) return rc; }
+    if (p->aov_mask & RT_AOV_TRI_ID) { if ((rc = ensure(c, &S.tri_id, &S.aov_px[1], npx))) return rc; }
+    if (p->aov_mask & RT_AOV_DEPTH) { if ((rc = ensure(c, &S.depth, &S.aov_px[2], npx))) return rc; }
     if (nd > 1 && gather == RT_GATHER_PEER_COPY) {
         for (int d = 1; d < nd; d++) {
             Dev& D = c->devs[d];
@@ -538,12 +554,11 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
     RtLaunchCfg cfg;
     cfg.block_threads = p->block_threads == 64 ? 64 : 128;
     // Defaults (profiles/r01_notes.md): small frames are bounded by the dependent chain of their longest pixels, which the
-    // 4-wide tree halves; large frames are throughput-bound, where the 2-wide tree with 32 warps/SM (64 registers) wins.
-    // "Small" is decided by the rays the previous frame of the same shape actually traced on this context (8 M per GPU),
-    // and by the pixel-sample count (4 M per GPU) for a first frame.
+    // wide tree shortens; large frames are throughput-bound.  "Small" is decided from the render parameters ONLY (pixel
+    // samples per GPU), never from what earlier frames did: two frames with equal parameters run the same kernel, on
+    // every rank of a partitioned render.
     const double px_per_part = (double)w * h * p->spp / (double)(part_count * (int)c->devs.size());
-    const bool same_shape = c->rays_w == w && c->rays_h == h && c->rays_spp == p->spp && c->rays_parts == part_count;
-    const bool small_frame = same_shape ? c->rays_per_dev <= 8.0e6 : px_per_part <= 4.0e6;
+    const bool small_frame = px_per_part <= 4.0e6;
     const bool want_wide = p->traversal == RT_TRAVERSAL_WIDE || (p->traversal == RT_TRAVERSAL_DEFAULT && small_frame);
     cfg.min_ctas = p->ctas_per_sm > 0 ? p->ctas_per_sm : (cfg.block_threads == 64 ? 12 : (want_wide ? 6 : 8));
     cfg.work_counters = (p->aov_mask & RT_AOV_WORK) != 0;
@@ -570,9 +585,9 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
             if (d == 0) {
                 fill_bgra_kernel<<<D0.sm_count * 4, 256, 0, D0.stream>>>(target, npx, make_uchar4(0, 0, 0, 255));
                 CK(c, cudaGetLastError());
-                if (p->aov_mask & RT_AOV_RGB_F32) CK(c, cudaMemsetAsync(D0.rgb, 0, 12 * npx, D0.stream));
-                if (p->aov_mask & RT_AOV_TRI_ID) CK(c, cudaMemsetAsync(D0.tri_id, 0xff, 4 * npx, D0.stream));
-                if (p->aov_mask & RT_AOV_DEPTH) CK(c, cudaMemsetAsync(D0.depth, 0, 4 * npx, D0.stream));
+                if (p->aov_mask & RT_AOV_RGB_F32) CK(c, cudaMemsetAsync(S.rgb, 0, 12 * npx, D0.stream));
+                if (p->aov_mask & RT_AOV_TRI_ID) CK(c, cudaMemsetAsync(S.tri_id, 0xff, 4 * npx, D0.stream));
+                if (p->aov_mask & RT_AOV_DEPTH) CK(c, cudaMemsetAsync(S.depth, 0, 4 * npx, D0.stream));
             }
             CK(c, cudaEventRecord(D.ev1[slot], D.stream));
             CK(c, cudaStreamWaitEvent(D.aux, D.ev1[slot], 0));
@@ -600,9 +615,9 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         f.n_sms = (unsigned)std::min(D.sm_count, RT_MAX_SMS);
         const bool local = (d > 0 && gather == RT_GATHER_PEER_COPY);
         f.bgra = local ? D.bgra : target; // peer-mapped for d > 0
-        f.rgb = (p->aov_mask & RT_AOV_RGB_F32) ? D0.rgb : nullptr;
-        f.tri_id = (p->aov_mask & RT_AOV_TRI_ID) ? D0.tri_id : nullptr;
-        f.depth = (p->aov_mask & RT_AOV_DEPTH) ? D0.depth : nullptr;
+        f.rgb = (p->aov_mask & RT_AOV_RGB_F32) ? S.rgb : nullptr;
+        f.tri_id = (p->aov_mask & RT_AOV_TRI_ID) ? S.tri_id : nullptr;
+        f.depth = (p->aov_mask & RT_AOV_DEPTH) ? S.depth : nullptr;
 
         int occ = 0, regs = 0;
         cudaError_t e = (p->mode == RT_MODE_STRICT) ? rt_occupancy_strict(cfg, &occ, &regs) : rt_occupancy_fast(cfg, &occ, &regs);
@@ -723,8 +738,6 @@ static int finish_frame(rt_ctx* c, int slot, rt_timing* tm)
             t.inner_visits += st[2];
             t.tri_tests += st[3];
         }
-        c->rays_per_dev = (double)(t.rays_closest + t.rays_shadow) / nd;
-        c->rays_w = S.width; c->rays_h = S.height; c->rays_spp = S.spp; c->rays_parts = S.part_count;
         t.gather_ms = S.gather_ms;
         t.total_ms = kmax + S.gather_ms;
         t.launches = S.launches;
@@ -799,9 +812,9 @@ int rt_download(rt_ctx* c, uint8_t* bgra, float* rgb, int32_t* tri_id, float* de
     if (tri_id && !(c->aov_mask & RT_AOV_TRI_ID)) return fail(c, RT_ERR_STATE, "rt_download: RT_AOV_TRI_ID was not rendered");
     if (depth_t && !(c->aov_mask & RT_AOV_DEPTH)) return fail(c, RT_ERR_STATE, "rt_download: RT_AOV_DEPTH was not rendered");
     if (bgra) CK(c, cudaMemcpyAsync(bgra, S.ipc_frame ? S.ipc_frame : S.bgra, npx * 4, cudaMemcpyDeviceToHost, D0.stream));
-    if (rgb) CK(c, cudaMemcpyAsync(rgb, D0.rgb, npx * 12, cudaMemcpyDeviceToHost, D0.stream));
-    if (tri_id) CK(c, cudaMemcpyAsync(tri_id, D0.tri_id, npx * 4, cudaMemcpyDeviceToHost, D0.stream));
-    if (depth_t) CK(c, cudaMemcpyAsync(depth_t, D0.depth, npx * 4, cudaMemcpyDeviceToHost, D0.stream));
+    if (rgb) CK(c, cudaMemcpyAsync(rgb, S.rgb, npx * 12, cudaMemcpyDeviceToHost, D0.stream));
+    if (tri_id) CK(c, cudaMemcpyAsync(tri_id, S.tri_id, npx * 4, cudaMemcpyDeviceToHost, D0.stream));
+    if (depth_t) CK(c, cudaMemcpyAsync(depth_t, S.depth, npx * 4, cudaMemcpyDeviceToHost, D0.stream));
     CK(c, cudaStreamSynchronize(D0.stream));
     return RT_OK;
 }

@@ -217,6 +217,7 @@ extern "C" {
 
 int rt_scene_load_obj(const char* obj_path, const char* mtl_path, const char* lights_path, rt_scene** out)
 {
+    return rt::guarded("rt_scene_load_obj", [&]() -> int {
     if (!obj_path || !mtl_path || !out) { rt::set_error("rt_scene_load_obj: null argument"); return RT_ERR_INVALID; }
     if (const char* e = std::getenv("RT_LOADER_SERIAL")) if (e[0] == '1') return load_obj_serial(obj_path, mtl_path, lights_path, out);
     std::string data;
@@ -353,6 +354,7 @@ int rt_scene_load_obj(const char* obj_path, const char* mtl_path, const char* li
     }
     *out = sc;
     return RT_OK;
+    });
 }
 
 int rt_scene_load_dir(const char* dir, rt_scene** out)
@@ -372,8 +374,17 @@ int rt_scene_load_rtsc(const char* path, rt_scene** out)
     float amb[4];
     bool ok = std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, "RTSC0001", 8) == 0 &&
               std::fread(hdr, 4, 4, f) == 4 && std::fread(amb, 4, 4, f) == 4;
-    rt_scene* sc = new rt_scene();
-    if (ok) {
+    if (ok) { // header counts against the file size: a corrupt header must not turn into a multi-GB allocation
+        const long here = std::ftell(f);
+        std::fseek(f, 0, SEEK_END);
+        const long end = std::ftell(f);
+        std::fseek(f, here, SEEK_SET);
+        const unsigned long long need = 40ull * hdr[0] + 36ull * hdr[1] + 24ull * hdr[2];
+        ok = here >= 0 && end >= here && need == (unsigned long long)(end - here);
+    }
+    rt_scene* sc = new (std::nothrow) rt_scene();
+    if (!sc) { std::fclose(f); rt::set_error("out of memory"); return RT_ERR_NOMEM; }
+    if (ok) try {
         sc->tri.resize(9 * (size_t)hdr[0]);
         sc->tri_mat.resize(hdr[0]);
         sc->mats.resize(9 * (size_t)hdr[1]);
@@ -384,7 +395,7 @@ int rt_scene_load_rtsc(const char* path, rt_scene** out)
              std::fread(sc->lights.data(), 4, sc->lights.size(), f) == sc->lights.size();
         for (uint32_t m : sc->tri_mat) ok = ok && m < hdr[1];
         std::memcpy(sc->ambient, amb, 12);
-    }
+    } catch (const std::bad_alloc&) { std::fclose(f); delete sc; rt::set_error(std::string(path) + ": out of memory"); return RT_ERR_NOMEM; }
     std::fclose(f);
     if (!ok) { delete sc; rt::set_error(std::string(path) + ": not a valid RTSC0001 scene pack"); return RT_ERR_IO; }
     *out = sc;
@@ -413,6 +424,7 @@ int rt_scene_save_rtsc(const rt_scene* s, const char* path)
 
 int rt_scene_from_arrays(const rt_scene_desc* d, rt_scene** out)
 {
+    return rt::guarded("rt_scene_from_arrays", [&]() -> int {
     if (!d || !out || (d->n_tris && (!d->tri_coords)) || (d->n_mats && !d->materials) || (d->n_lights && !d->lights)) {
         rt::set_error("rt_scene_from_arrays: null argument");
         return RT_ERR_INVALID;
@@ -433,10 +445,12 @@ int rt_scene_from_arrays(const rt_scene_desc* d, rt_scene** out)
     }
     *out = sc;
     return RT_OK;
+    });
 }
 
 int rt_scene_soup(uint32_t n_tris, uint32_t seed, rt_scene** out)
 {
+    return rt::guarded("rt_scene_soup", [&]() -> int {
     if (!out || !n_tris) { rt::set_error("rt_scene_soup: bad argument"); return RT_ERR_INVALID; }
     rt_scene* sc = new rt_scene();
     sc->tri.resize(9 * (size_t)n_tris);
@@ -458,11 +472,13 @@ int rt_scene_soup(uint32_t n_tris, uint32_t seed, rt_scene** out)
     }
     *out = sc;
     return RT_OK;
+    });
 }
 
 int rt_scene_instance_grid(const rt_scene* base, uint32_t nx, uint32_t ny, uint32_t nz, const float pitch[3],
                            uint32_t light_every, rt_scene** out)
 {
+    return rt::guarded("rt_scene_instance_grid", [&]() -> int {
     if (!base || !out || !pitch || !nx || !ny || !nz) { rt::set_error("rt_scene_instance_grid: bad argument"); return RT_ERR_INVALID; }
     const uint64_t copies = (uint64_t)nx * ny * nz;
     const uint64_t total = copies * base->n_tris();
@@ -495,6 +511,7 @@ int rt_scene_instance_grid(const rt_scene* base, uint32_t nx, uint32_t ny, uint3
             }
     *out = sc;
     return RT_OK;
+    });
 }
 
 int rt_scene_view(const rt_scene* s, rt_scene_desc* out)
@@ -519,9 +536,11 @@ void rt_scene_free(rt_scene* s) { delete s; }
 
 int rt_scene_build_bvh(rt_scene* s, int heuristic)
 {
+    return rt::guarded("rt_scene_build_bvh", [&]() -> int {
     if (!s) { rt::set_error("rt_scene_build_bvh: null scene"); return RT_ERR_INVALID; }
     const rt::BvhArith arith = (heuristic & RT_BVH_REFBIN) ? rt::BVH_REFBIN : rt::BVH_IEEE;
     return rt::build_bvh(*s, heuristic & ~RT_BVH_REFBIN, arith, 0);
+    });
 }
 
 } // extern "C"

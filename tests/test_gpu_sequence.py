@@ -150,3 +150,24 @@ def test_sequence_error_paths(rt, gpu_scenes):
         fresh.packed_tiles()
     assert e.value.code == rt.RT_ERR_STATE
     fresh.close(); buf.close()
+
+
+def test_aovs_belong_to_their_frame_slot(rt, gpu_scenes):
+    """AOV buffers are per frame slot — a render queued on slot 1 must not overwrite what rt_download returns for
+    slot 0 (they used to be shared by the context)."""
+    _, ctx = gpu_scenes["car_boxed"]
+    w, h = 320, 180
+    aov = rt.RT_AOV_RGB_F32 | rt.RT_AOV_TRI_ID | rt.RT_AOV_DEPTH
+    cs = cams(2)
+    want = []
+    for cam in cs:
+        ctx.render_frame(rt.default_params(width=w, height=h, cam=cam, aov_mask=aov))
+        want.append({k: v.copy() for k, v in ctx.load_from_gpu(rgb=True, tri_id=True, depth=True).items()})
+    assert not np.array_equal(want[0]["id"], want[1]["id"])
+    for s in (0, 1):
+        ctx.render_frame_async(rt.default_params(width=w, height=h, cam=cs[s], aov_mask=aov, frame_slot=s))
+    ctx.frame_wait(1)
+    ctx.frame_wait(0)   # slot 0 is now "the last finished render": rt_download must return ITS AOVs
+    got = ctx.load_from_gpu(rgb=True, tri_id=True, depth=True)
+    for k in ("bgra", "id", "depth", "rgb"):
+        assert np.array_equal(got[k], want[0][k]), k
