@@ -151,7 +151,8 @@ enum { /* rt_render_params.traversal */
     RT_TRAVERSAL_DEFAULT = 0,
     RT_TRAVERSAL_PLAIN = 1,       /* while-while in the reference's visit order */
     RT_TRAVERSAL_SPECULATIVE = 2, /* 2-wide tree, postponed leaves: same image, more lanes busy */
-    RT_TRAVERSAL_WIDE = 3         /* 4-wide collapse of the reference tree + postponed leaves (default when it fits) */
+    RT_TRAVERSAL_WIDE = 3,        /* 4-wide collapse of the reference tree + postponed leaves */
+    RT_TRAVERSAL_WIDE8 = 4        /* compressed 8-wide collapse (96-byte nodes, 8-bit outward-rounded child boxes, csrc/wide8.h) */
 };
 
 enum { /* rt_render_params.gather */
@@ -188,7 +189,10 @@ typedef struct rt_render_params {
     int32_t   traversal;        /* RT_TRAVERSAL_* (fast mode only; strict always walks the reference order) */
     int32_t   frame_flags;      /* RT_FRAME_* */
     int32_t   frame_slot;       /* which of the context's RT_FRAME_SLOTS device frames to render into (frame sequences) */
-    int32_t   reserved[2];
+    /* fast build on the compressed 8-wide tree (0 = library default, < 0 = off): */
+    int32_t   drain_k;          /* once the chunk queue is empty, a warp left with <= drain_k live pixels hands them to the
+                                   cooperative drain kernel (eight lanes per ray); default 8 */
+    int32_t   cull;             /* test every 8x4-pixel chunk's ray pyramid against the top of the tree first; default on */
 } rt_render_params;
 
 typedef struct rt_timing {
@@ -273,6 +277,9 @@ int rt_debug_set_tile_order(rt_ctx* ctx, const unsigned* tiles, int n);
  * (96 B per compressed 8-wide node, csrc/wide8.h).
  * out may be NULL to query the size; meta4 receives {max_depth, stack_need4, n_lights, depth8}. */
 int rt_debug_flatten_host(const rt_scene_desc* desc, int which, void* out, size_t cap_bytes, size_t* bytes_out, int* meta4);
+/* Diagnostics: copy of a scene array as it lies on the context's first device (same selectors; 0 nodes, 1 nodes4, 2 tris, 3 shade,
+ * 7 nodes8): lets a test compare the device-side flatten of rt_create_gpu with the host staging arrays byte for byte. */
+int rt_debug_device_array(rt_ctx* ctx, int which, void* out, size_t cap_bytes, size_t* bytes_out);
 /* Roofline microbenchmark: GB/s of random 64-byte-record gathers (the shape of a node fetch, one record per
  * lane) from a working set of ws_bytes on `device` — L1-, L2- or HBM-resident depending on the size. */
 int rt_debug_gather_bandwidth(int device, size_t ws_bytes, float* gbs_out);

@@ -31,7 +31,7 @@ RT_MODE_FAST, RT_MODE_STRICT = 0, 1
 RT_AOV_RGB_F32, RT_AOV_TRI_ID, RT_AOV_DEPTH, RT_AOV_WORK = 1, 2, 4, 8
 RT_GATHER_PEER_STORE, RT_GATHER_PEER_COPY = 0, 1
 RT_BVH_REFBIN = 0x100
-RT_TRAVERSAL_DEFAULT, RT_TRAVERSAL_PLAIN, RT_TRAVERSAL_SPECULATIVE, RT_TRAVERSAL_WIDE = 0, 1, 2, 3
+RT_TRAVERSAL_DEFAULT, RT_TRAVERSAL_PLAIN, RT_TRAVERSAL_SPECULATIVE, RT_TRAVERSAL_WIDE, RT_TRAVERSAL_WIDE8 = 0, 1, 2, 3, 4
 RT_TILE_W, RT_TILE_H = 16, 8
 RT_MAX_DEVICES = 16
 RT_FRAME_SLOTS = 2
@@ -45,7 +45,7 @@ EXPORTS = [
     "rt_part_tile_count", "rt_packed_tiles", "rt_unpack_tiles", "rt_frame_ipc_export", "rt_frame_ipc_import",
     "rt_frame_device_ptr", "rt_write_bmp", "rt_abi_version", "rt_device_count", "rt_debug_warp_trace",
     "rt_render_async", "rt_download_async", "rt_frame_wait", "rt_host_alloc", "rt_host_free",
-    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order", "rt_scene_build_bvh_gpu", "rt_debug_gather_bandwidth", "rt_create_gpu", "rt_debug_flatten_host",
+    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order", "rt_scene_build_bvh_gpu", "rt_debug_gather_bandwidth", "rt_create_gpu", "rt_debug_flatten_host", "rt_debug_device_array",
 ]
 
 
@@ -75,7 +75,7 @@ class rt_render_params(C.Structure):
                 ("gather", C.c_int32), ("part_index", C.c_int32), ("part_count", C.c_int32),
                 ("block_threads", C.c_int32), ("ctas_per_sm", C.c_int32), ("refill_threshold", C.c_int32),
                 ("traversal", C.c_int32), ("frame_flags", C.c_int32), ("frame_slot", C.c_int32),
-                ("reserved", C.c_int32 * 2)]
+                ("drain_k", C.c_int32), ("cull", C.c_int32)]
 
 
 class rt_timing(C.Structure):
@@ -128,6 +128,7 @@ def lib() -> C.CDLL:
     L.rt_create.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(i32), i32, C.POINTER(vp)]
     L.rt_debug_flatten_host.argtypes = [C.POINTER(rt_scene_desc), i32, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(i32)]
     L.rt_create_gpu.argtypes = [vp, i32, C.POINTER(i32), i32, i32, C.POINTER(vp), C.POINTER(rt_bvh_gpu_stats)]
+    L.rt_debug_device_array.argtypes = [vp, i32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.rt_render.argtypes = [vp, C.POINTER(rt_render_params), C.POINTER(rt_timing)]
     L.rt_download.argtypes = [vp, vp, vp, vp, vp]
     L.rt_destroy.argtypes = [vp]; L.rt_destroy.restype = None
@@ -395,6 +396,14 @@ class Context:
     def frame_ipc_import(self, handle: bytes, width, height, slot=0):
         buf = C.create_string_buffer(handle, 64)
         _check(lib().rt_frame_ipc_import_slot(self._h, slot, buf, width, height), self._h)
+
+    def device_array(self, which: int, dtype=np.uint32) -> np.ndarray:
+        """Diagnostics: copy of a scene array as it lies on the context's first device (7 = nodes8)."""
+        n = C.c_size_t()
+        _check(lib().rt_debug_device_array(self._h, which, None, 0, C.byref(n)), self._h)
+        a = np.empty(n.value // np.dtype(dtype).itemsize, dtype)
+        _check(lib().rt_debug_device_array(self._h, which, _ptr(a), a.nbytes, C.byref(n)), self._h)
+        return a
 
     def warp_trace(self, enable=True, max_warps=8192):
         """Diagnostics: arm / read the per-warp timeline of RT_AOV_WORK renders (see rt_debug_warp_trace)."""

@@ -25,6 +25,8 @@
 //           computing them per test, and never normalised.  A test reads the
 //           first 48 bytes (one 256-bit + one 128-bit load); q3 is read once per ray, on a hit.
 //           64-byte records keep every 256-bit load 32-byte aligned.
+//   nodes8  the fast build's default tree: the reference tree collapsed to 8-wide nodes of 96 bytes with child boxes
+//           quantised to 8 bits per plane, rounded outward (layout and rules: wide8.h)
 //   shade[orig]   (unit normal norm[0].xyz, material index as int bits); norm[1] == -norm[0]
 //   mats    3 x float4 per material: (ks, 0) (kd, 0) (kr, |kr| > 0 ? 1 : 0)
 //   lights  2 x float4 per light: (pos, 0) (kl, 0)
@@ -40,11 +42,13 @@
 #define RT_LEAF_CNT_ESC 15
 #define RT_STACK_ENTRIES 40   /* sentinel + reference depth cap 32 (cpu/include/options.h:64) + postponed leaf */
 #define RT_STACK_ENTRIES_WIDE 48 /* 4-wide tree: up to three siblings stay pushed per level */
+#define RT_STACK8_ENTRIES 40     /* 8-wide tree: one (node, remaining-children mask) group per level, 8 bytes each */
 #define RT_MAX_BOUNCES 8
 
 struct RtDeviceScene {
     const float4* nodes;
     const float4* nodes4;   // 4-wide collapse (fast build), 8 x float4 per node
+    const uint4*  nodes8;   // compressed 8-wide collapse (fast build), 96 bytes = 6 x uint4 per node (wide8.h); may be null
     const float4* tris;
     const float4* shade;
     const float4* mats;
@@ -53,6 +57,18 @@ struct RtDeviceScene {
     int   n_lights;
     float amb[3];
 };
+
+// A path handed from the per-lane render kernel to the cooperative drain kernel (render_kernel.cuh: drain_kernel): the
+// pixel, what has been accumulated so far, and the ray that was in flight (it is traced again from its start).
+struct RtPathRec {
+    int   pix, sample, depth, kind;
+    float acc[3], col[3], thr[3];
+    float o[3], d[3];
+    float ld2;
+    float P[3], n[3], in[3], pend[3];
+    int   mat, li, culled, pad;
+};
+#define RT_DRAIN_STACK 96 /* per-path stack of the drain kernel: (child ref, entry distance) pairs, up to 7 per level */
 
 struct RtFrameArgs {
     // camera basis exactly as thread_render derives it (cpu/src/main.c:241-250)
@@ -67,6 +83,14 @@ struct RtFrameArgs {
     unsigned long long* sm_cursor; // RT_OPT_SMQUEUE: one work cursor per SM (indexed by %smid), zeroed per frame
     unsigned n_sms;
     int   refill_threshold;
+    int   cull;                    // fast build: test every chunk's ray pyramid against the top of nodes8 first (needs sc.nodes8)
+    // fast build, tail of the frame: once the chunk queue is empty, a warp left with <= drain_k live pixels writes their
+    // paths to drain_queue and exits; drain_kernel finishes them with eight lanes per ray (0 = off)
+    int   drain_k;
+    unsigned drain_cap;            // records drain_queue can hold
+    RtPathRec* drain_queue;
+    unsigned* drain_count;         // records written (render kernel) / to process (drain kernel)
+    unsigned* drain_next;          // drain kernel: next record to hand out
     // outputs (bgra may be a peer-mapped pointer into device 0's frame)
     uchar4* bgra;
     float*  rgb;                   // optional

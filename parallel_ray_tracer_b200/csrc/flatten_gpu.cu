@@ -11,12 +11,15 @@
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <cmath>
 #include <string>
+#include <vector>
 
 #include "device_layout.h"
 #include "gpu_tree.h"
 #include "staged_copy.h"
+#include "wide8.h"
 
 namespace {
 
@@ -154,6 +157,56 @@ __global__ void need4_kernel(int n4, const float4* __restrict__ nodes4, const un
     need4[k] = max(live - 1, 0) + deepest;
 }
 
+// ---- compressed 8-wide tree (wide8.h), level by level exactly as wide8.cpp builds it on the host ----
+// pass A: inner children per node of the level
+__global__ void w8_count_kernel(int n, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, int* __restrict__ n_inner)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rt::W8Child ch[8];
+    const int c = rt::w8_expand(bvh, level[i], ch);
+    int k = 0;
+    for (int j = 0; j < c; j++) k += ch[j].inner;
+    n_inner[i] = k;
+}
+// pass B: the next level's node list (inner children in slot order, the order their indices are assigned in)
+__global__ void w8_next_kernel(int n, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, const int* __restrict__ offset,
+                               unsigned* __restrict__ next)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rt::W8Child ch[8];
+    int slot_of[8];
+    const int c = rt::w8_expand(bvh, level[i], ch);
+    rt::w8_assign_slots(ch, c, slot_of);
+    int m = 0;
+    for (int s = 0; s < 8; s++)
+        for (int j = 0; j < c; j++)
+            if (slot_of[j] == s && ch[j].inner) next[offset[i] + m++] = (unsigned)ch[j].bnode;
+}
+// pass C: the records of the level
+__global__ void w8_encode_kernel(int n, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, const int* __restrict__ offset,
+                                 unsigned base, unsigned next_base, unsigned* __restrict__ words)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rt::W8Child ch[8];
+    int slot_of[8];
+    int32_t ref_of[8];
+    const int c = rt::w8_expand(bvh, level[i], ch);
+    rt::w8_assign_slots(ch, c, slot_of);
+    for (int j = 0; j < c; j++) ref_of[j] = ch[j].inner ? 0 : rt::w8_leaf_ref(ch[j].first, ch[j].cnt);
+    int m = 0;
+    for (int s = 0; s < 8; s++)
+        for (int j = 0; j < c; j++)
+            if (slot_of[j] == s && ch[j].inner) ref_of[j] = (int32_t)(next_base + (unsigned)offset[i] + (unsigned)m++);
+    uint32_t w[rt::kWide8Words];
+    rt::w8_encode(ch, c, slot_of, ref_of, w);
+    uint4* o = reinterpret_cast<uint4*>(words + (size_t)(base + (unsigned)i) * rt::kWide8Words);
+#pragma unroll
+    for (int k = 0; k < 6; k++) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+}
+
 struct Buf {
     void* p = nullptr;
     ~Buf() { cudaFree(p); }
@@ -218,9 +271,57 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
     CKF(cudaGetLastError());
     int need_root = 0;
     CKF(cudaMemcpy(&need_root, need4.p, 4, cudaMemcpyDeviceToHost));
+    // ---- compressed 8-wide tree: first the node lists of all levels (sizes), then the records ----
+    Buf nodes8;
+    size_t n8 = 0;
+    int depth8 = 0;
+    {
+        std::vector<Buf> lists, offs;   // per level: node list, exclusive scan of the inner-child counts
+        std::vector<int> sizes;
+        lists.reserve(72); offs.reserve(72);  // (Buf is not movable: no reallocation; at most 66 levels, checked below)
+        lists.emplace_back();
+        CKF(lists[0].alloc(4));
+        CKF(cudaMemset(lists[0].p, 0, 4)); // level 0 = {reference node 0}
+        sizes.push_back(1);
+        Buf cnt, tmp;
+        size_t tmp_cap = 0;
+        for (int lv = 0; sizes[lv] > 0; lv++) {
+            if (lv > 64) { err = "flatten_gpu: 8-wide tree deeper than 64 levels"; return RT_ERR_INVALID; }
+            const int m = sizes[lv];
+            Buf c2;
+            CKF(c2.alloc(((size_t)m + 1) * 4));
+            CKF(cudaMemset(c2.p, 0, ((size_t)m + 1) * 4));
+            w8_count_kernel<<<(m + 127) / 128, 128>>>(m, lists[lv].as<unsigned>(), t.nodes, c2.as<int>());
+            offs.emplace_back();
+            CKF(offs[lv].alloc(((size_t)m + 1) * 4));
+            size_t need = 0;
+            CKF(cub::DeviceScan::ExclusiveSum(nullptr, need, c2.as<int>(), offs[lv].as<int>(), m + 1));
+            if (need > tmp_cap) { cudaFree(tmp.p); tmp.p = nullptr; CKF(tmp.alloc(need)); tmp_cap = need; }
+            CKF(cub::DeviceScan::ExclusiveSum(tmp.p, need, c2.as<int>(), offs[lv].as<int>(), m + 1));
+            int total = 0;
+            CKF(cudaMemcpy(&total, offs[lv].as<int>() + m, 4, cudaMemcpyDeviceToHost));
+            lists.emplace_back();
+            CKF(lists[lv + 1].alloc((size_t)std::max(total, 1) * 4));
+            if (total > 0) w8_next_kernel<<<(m + 127) / 128, 128>>>(m, lists[lv].as<unsigned>(), t.nodes, offs[lv].as<int>(), lists[lv + 1].as<unsigned>());
+            CKF(cudaGetLastError());
+            sizes.push_back(total);
+            n8 += (size_t)m;
+            depth8++;
+        }
+        CKF(nodes8.alloc(n8 * 96));
+        size_t base = 0;
+        for (int lv = 0; lv < depth8; lv++) {
+            const int m = sizes[lv];
+            w8_encode_kernel<<<(m + 127) / 128, 128>>>(m, lists[lv].as<unsigned>(), t.nodes, offs[lv].as<int>(), (unsigned)base, (unsigned)(base + (size_t)m),
+                                                       nodes8.as<unsigned>());
+            base += (size_t)m;
+        }
+        CKF(cudaGetLastError());
+    }
     CKF(cudaDeviceSynchronize());
     out.nodes = nodes.take<float4>(); out.nodes4 = nodes4.take<float4>(); out.tris = tris.take<float4>(); out.shade = shade.take<float4>();
     out.leaf_cnt = fl.need_leaf_cnt ? leaf_cnt.take<int>() : nullptr;
+    out.nodes8 = nodes8.take<uint4>(); out.n_nodes8 = n8; out.depth8 = depth8;
     out.n_inner = n_inner; out.n_nodes4 = (size_t)n4; out.n_tris = (size_t)n;
     out.max_depth = fl.max_depth;
     out.stack_need4 = need_root + 3; // + sentinel, postponed leaf, slack (flatten.cpp)

@@ -42,10 +42,11 @@ int gpu_build_bvh(rt_scene& s, int refbin, int device, rt_bvh_gpu_stats* stats, 
 // as flatten_scene (flatten.cpp) makes on the host.  Pointers are owned by the caller (cudaFree).
 struct DeviceFlat {
     float4 *nodes = nullptr, *nodes4 = nullptr, *tris = nullptr, *shade = nullptr;
+    uint4* nodes8 = nullptr;
     int* leaf_cnt = nullptr;
-    size_t n_inner = 0, n_nodes4 = 0, n_tris = 0;
-    int max_depth = 0, stack_need4 = 0;
-    size_t bytes() const { return 64 * n_inner + 128 * n_nodes4 + 64 * n_tris + 16 * n_tris + (leaf_cnt ? 4 * n_tris : 0); }
+    size_t n_inner = 0, n_nodes4 = 0, n_nodes8 = 0, n_tris = 0;
+    int max_depth = 0, stack_need4 = 0, depth8 = 0;
+    size_t bytes() const { return 64 * n_inner + 128 * n_nodes4 + 96 * n_nodes8 + 64 * n_tris + 16 * n_tris + (leaf_cnt ? 4 * n_tris : 0); }
 };
 int flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_mats, DeviceFlat& out, std::string& err);
 

@@ -12,3 +12,19 @@ cudaError_t rt_occupancy_fast(const RtLaunchCfg& cfg, int* ctas_per_sm, int* reg
 {
     return rt_fast::occupancy(cfg, ctas_per_sm, regs);
 }
+
+cudaError_t rt_launch_drain(const RtDeviceScene& sc, const RtFrameArgs& fa, bool work_counters, int sm_count, cudaStream_t st)
+{
+    static int occ[2] = {0, 0};
+    const int w = work_counters ? 1 : 0;
+    if (!occ[w]) {
+        cudaError_t e = work_counters ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[w], rt_fast::drain_kernel<true>, 128, 0)
+                                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[w], rt_fast::drain_kernel<false>, 128, 0);
+        if (e != cudaSuccess) return e;
+        if (occ[w] < 1) occ[w] = 1;
+    }
+    const int grid = sm_count * occ[w];
+    if (work_counters) rt_fast::drain_kernel<true><<<grid, 128, 0, st>>>(sc, fa);
+    else rt_fast::drain_kernel<false><<<grid, 128, 0, st>>>(sc, fa);
+    return cudaGetLastError();
+}

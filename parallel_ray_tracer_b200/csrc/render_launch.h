@@ -8,7 +8,7 @@ struct RtLaunchCfg {
     int min_ctas;       // __launch_bounds__ second argument: caps registers/thread
     bool work_counters; // RT_AOV_WORK build (counts inner visits and triangle tests)
     bool speculative;   // fast build: speculative traversal (postponed leaves)
-    bool wide;          // fast build: 4-wide tree (implies speculative)
+    int wide;           // fast build: 0 = the reference's 2-wide tree, 1 = its 4-wide collapse, 2 = compressed 8-wide (both imply speculative)
     int grid;           // number of persistent CTAs
 };
 
@@ -17,3 +17,5 @@ cudaError_t rt_launch_strict(const RtDeviceScene& sc, const RtFrameArgs& fa, con
 // resident CTAs per SM and registers/thread of the instantiation cfg selects
 cudaError_t rt_occupancy_fast(const RtLaunchCfg& cfg, int* ctas_per_sm, int* regs);
 cudaError_t rt_occupancy_strict(const RtLaunchCfg& cfg, int* ctas_per_sm, int* regs);
+// the cooperative drain kernel (fast build): finishes the paths queued in fa.drain_queue; one resident wave
+cudaError_t rt_launch_drain(const RtDeviceScene& sc, const RtFrameArgs& fa, bool work_counters, int sm_count, cudaStream_t st);

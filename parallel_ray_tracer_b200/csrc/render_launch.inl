@@ -5,7 +5,7 @@ namespace RT_KERNEL_NS {
 
 typedef void (*kernel_fn)(const RtDeviceScene, const RtFrameArgs);
 
-template <bool WORK, bool SPEC, bool WIDE>
+template <bool WORK, bool SPEC, int WIDE>
 static kernel_fn pick(int block, int minb)
 {
     if (block == 64) return render_kernel<64, 12, WORK, SPEC, WIDE>;
@@ -24,11 +24,12 @@ static kernel_fn pick(const RtLaunchCfg& c)
 {
 #if RT_STRICT
     // the strict build never speculates and never uses the 4-wide tree: its visit order is the reference's
-    return c.work_counters ? pick<true, false, false>(c.block_threads, c.min_ctas) : pick<false, false, false>(c.block_threads, c.min_ctas);
+    return c.work_counters ? pick<true, false, 0>(c.block_threads, c.min_ctas) : pick<false, false, 0>(c.block_threads, c.min_ctas);
 #else
-    if (c.wide) return c.work_counters ? pick<true, true, true>(c.block_threads, c.min_ctas) : pick<false, true, true>(c.block_threads, c.min_ctas);
-    if (c.speculative) return c.work_counters ? pick<true, true, false>(c.block_threads, c.min_ctas) : pick<false, true, false>(c.block_threads, c.min_ctas);
-    return c.work_counters ? pick<true, false, false>(c.block_threads, c.min_ctas) : pick<false, false, false>(c.block_threads, c.min_ctas);
+    if (c.wide == 2) return c.work_counters ? pick<true, true, 2>(c.block_threads, c.min_ctas) : pick<false, true, 2>(c.block_threads, c.min_ctas);
+    if (c.wide == 1) return c.work_counters ? pick<true, true, 1>(c.block_threads, c.min_ctas) : pick<false, true, 1>(c.block_threads, c.min_ctas);
+    if (c.speculative) return c.work_counters ? pick<true, true, 0>(c.block_threads, c.min_ctas) : pick<false, true, 0>(c.block_threads, c.min_ctas);
+    return c.work_counters ? pick<true, false, 0>(c.block_threads, c.min_ctas) : pick<false, false, 0>(c.block_threads, c.min_ctas);
 #endif
 }
 

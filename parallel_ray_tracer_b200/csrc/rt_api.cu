@@ -37,6 +37,8 @@ struct Dev {
     cudaEvent_t ev0[RT_FRAME_SLOTS] = {}, ev1[RT_FRAME_SLOTS] = {}, ev_done[RT_FRAME_SLOTS] = {}, ev2 = nullptr;
     // scene (replicated per device)
     float4 *nodes = nullptr, *nodes4 = nullptr, *tris = nullptr, *shade = nullptr, *mats = nullptr, *lights = nullptr;
+    uint4* nodes8 = nullptr; // compressed 8-wide tree (wide8.h); null when the context has none
+    size_t bytes[8] = {};    // sizes of the scene arrays, by rt_debug_flatten_host selector
     int* leaf_cnt = nullptr;
     // per-frame control block, one per frame slot (RT_CTRL_WORDS u64 each): [0..3] stats, [4] tile counter, [8..] SM cursors
     unsigned long long* ctrl = nullptr;
@@ -52,6 +54,8 @@ struct Dev {
     uchar4* packed = nullptr; // packed tiles (gather paths)
     size_t packed_px = 0;
     bool peer_to_0 = false;
+    RtPathRec* drain_queue[RT_FRAME_SLOTS] = {}; // tail hand-off queue per frame slot (render_kernel.cuh: drain_kernel)
+    size_t drain_cap[RT_FRAME_SLOTS] = {};
     unsigned long long* warp_trace = nullptr; // diagnostics (rt_debug_warp_trace)
     size_t warp_trace_cap = 0;
     int warp_trace_n = 0;
@@ -101,7 +105,7 @@ struct rt_ctx {
     uchar4* gather_buf = nullptr; // in-process PEER_COPY landing zone on device 0
     size_t gather_px = 0;
     size_t scene_bytes = 0;
-    int max_depth = 0, stack_need4 = 0;
+    int max_depth = 0, stack_need4 = 0, depth8 = 0;
     bool want_trace = false;
 };
 
@@ -263,9 +267,10 @@ int setup_local_index(rt_ctx* c, int w, int h, int parts)
 void free_dev(Dev& D)
 {
     cudaSetDevice(D.id);
-    cudaFree(D.nodes); cudaFree(D.nodes4); cudaFree(D.tris); cudaFree(D.shade); cudaFree(D.mats); cudaFree(D.lights);
+    cudaFree(D.nodes); cudaFree(D.nodes4); cudaFree(D.nodes8); cudaFree(D.tris); cudaFree(D.shade); cudaFree(D.mats); cudaFree(D.lights);
     cudaFree(D.leaf_cnt); cudaFree(D.ctrl); cudaFree(D.tile_list); cudaFree(D.warp_trace);
     cudaFree(D.bgra); cudaFree(D.packed);
+    for (int s = 0; s < RT_FRAME_SLOTS; s++) cudaFree(D.drain_queue[s]);
     if (D.ctrl_host) cudaFreeHost(D.ctrl_host);
     for (int s = 0; s < RT_FRAME_SLOTS; s++) {
         if (D.ev0[s]) cudaEventDestroy(D.ev0[s]);
@@ -326,6 +331,7 @@ static int create_common(const rt::FlatScene& flat, rt::DeviceFlat* pre, const i
     c->scene_bytes = pre ? pre->bytes() + 4 * (flat.mats.size() + flat.lights.size()) : flat.bytes();
     c->max_depth = pre ? pre->max_depth : flat.max_depth;
     c->stack_need4 = pre ? pre->stack_need4 : flat.stack_need4;
+    c->depth8 = pre ? pre->depth8 : flat.depth8;
     c->scene_host_view.n_lights = (int)flat.n_lights;
     std::memcpy(c->scene_host_view.amb, flat.ambient, 12);
     c->devs.resize(ndev);
@@ -334,6 +340,7 @@ static int create_common(const rt::FlatScene& flat, rt::DeviceFlat* pre, const i
     const size_t b_nodes = pre ? 64 * pre->n_inner : flat.nodes.size() * 4, b_nodes4 = pre ? 128 * pre->n_nodes4 : flat.nodes4.size() * 4;
     const size_t b_tris = pre ? 64 * pre->n_tris : flat.tris.size() * 4, b_shade = pre ? 16 * pre->n_tris : flat.shade.size() * 4;
     const size_t b_leaf = pre ? (pre->leaf_cnt ? 4 * pre->n_tris : 0) : flat.leaf_cnt.size() * 4;
+    const size_t b_nodes8 = pre ? 96 * pre->n_nodes8 : flat.nodes8.size() * 4;
     for (int i = 0; i < ndev; i++) {
         Dev& D = c->devs[i];
         D.id = devices[i];
@@ -371,16 +378,19 @@ static int create_common(const rt::FlatScene& flat, rt::DeviceFlat* pre, const i
         Dev& Z = c->devs[0];
         if (i == 0 && pre) { // adopt the arrays the device-side flatten left on this device
             D.nodes = pre->nodes; D.nodes4 = pre->nodes4; D.tris = pre->tris; D.shade = pre->shade; D.leaf_cnt = pre->leaf_cnt;
-            pre->nodes = pre->nodes4 = pre->tris = pre->shade = nullptr; pre->leaf_cnt = nullptr;
+            D.nodes8 = pre->nodes8;
+            pre->nodes = pre->nodes4 = pre->tris = pre->shade = nullptr; pre->leaf_cnt = nullptr; pre->nodes8 = nullptr;
         } else {
             CKC(put(&D.nodes, flat.nodes.data(), &Z.nodes, b_nodes));
             CKC(put(&D.nodes4, flat.nodes4.data(), &Z.nodes4, b_nodes4));
+            CKC(put(&D.nodes8, flat.nodes8.data(), &Z.nodes8, b_nodes8));
             CKC(put(&D.tris, flat.tris.data(), &Z.tris, b_tris));
             CKC(put(&D.shade, flat.shade.data(), &Z.shade, b_shade));
             CKC(put(&D.leaf_cnt, flat.leaf_cnt.data(), &Z.leaf_cnt, b_leaf));
         }
         CKC(put(&D.mats, flat.mats.data(), &Z.mats, flat.mats.size() * 4));
         CKC(put(&D.lights, flat.lights.data(), &Z.lights, flat.lights.size() * 4));
+        D.bytes[0] = b_nodes; D.bytes[1] = b_nodes4; D.bytes[2] = b_tris; D.bytes[3] = b_shade; D.bytes[4] = b_leaf; D.bytes[7] = b_nodes8;
         CKC(cudaMalloc((void**)&D.ctrl, 8 * RT_CTRL_WORDS * RT_FRAME_SLOTS));
         CKC(cudaMallocHost((void**)&D.ctrl_host, 64 * RT_FRAME_SLOTS));
         if (i == 0) CKC(cudaStreamSynchronize(D.stream)); // the fan-out below reads device 0's arrays
@@ -454,11 +464,11 @@ int rt_create_gpu(rt_scene* s, int heuristic, const int* devices, int ndev, int 
     rc = rt::flatten_gpu(tree, s->tri_mat.empty() ? nullptr : s->tri_mat.data(), s->n_mats(), df, err);
     tree.release();
     if (rc) {
-        cudaFree(df.nodes); cudaFree(df.nodes4); cudaFree(df.tris); cudaFree(df.shade); cudaFree(df.leaf_cnt);
+        cudaFree(df.nodes); cudaFree(df.nodes4); cudaFree(df.nodes8); cudaFree(df.tris); cudaFree(df.shade); cudaFree(df.leaf_cnt);
         return fail(nullptr, rc, "rt_create_gpu: " + err);
     }
     rc = create_common(small, &df, devices, ndev, out);
-    cudaFree(df.nodes); cudaFree(df.nodes4); cudaFree(df.tris); cudaFree(df.shade); cudaFree(df.leaf_cnt); // (null once adopted)
+    cudaFree(df.nodes); cudaFree(df.nodes4); cudaFree(df.nodes8); cudaFree(df.tris); cudaFree(df.shade); cudaFree(df.leaf_cnt); // (null once adopted)
     return rc;
     });
 }
@@ -559,12 +569,23 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
     // every rank of a partitioned render.
     const double px_per_part = (double)w * h * p->spp / (double)(part_count * (int)c->devs.size());
     const bool small_frame = px_per_part <= 4.0e6;
-    const bool want_wide = p->traversal == RT_TRAVERSAL_WIDE || (p->traversal == RT_TRAVERSAL_DEFAULT && small_frame);
-    cfg.min_ctas = p->ctas_per_sm > 0 ? p->ctas_per_sm : (cfg.block_threads == 64 ? 12 : (want_wide ? 6 : 8));
+    // fast build: which tree to walk.  The compressed 8-wide tree when the context has one and its depth fits the group
+    // stack; RT_TRAVERSAL_* pins a variant (the strict build always walks the reference's own 2-wide order).
+    const bool have8 = c->devs[0].nodes8 != nullptr && c->depth8 + 2 <= RT_STACK8_ENTRIES;
+    const bool have4 = c->stack_need4 <= RT_STACK_ENTRIES_WIDE;
+    int wide = 0;
+    if (p->traversal == RT_TRAVERSAL_WIDE8) wide = have8 ? 2 : (have4 ? 1 : 0);
+    else if (p->traversal == RT_TRAVERSAL_WIDE) wide = have4 ? 1 : 0;
+    else if (p->traversal == RT_TRAVERSAL_DEFAULT) wide = small_frame ? (have4 ? 1 : 0) : 0;
+    cfg.min_ctas = p->ctas_per_sm > 0 ? p->ctas_per_sm : (cfg.block_threads == 64 ? 12 : (wide ? 6 : 8));
     cfg.work_counters = (p->aov_mask & RT_AOV_WORK) != 0;
     cfg.speculative = p->traversal != RT_TRAVERSAL_PLAIN;
-    // (the 4-wide tree is only used when its worst-case stack need fits the shared stack)
-    cfg.wide = want_wide && c->stack_need4 <= RT_STACK_ENTRIES_WIDE;
+    cfg.wide = wide;
+    // tail of the frame on the compressed tree: chunk culling and the cooperative drain kernel (defaults on; < 0 = off)
+    const bool tree8 = p->mode == RT_MODE_FAST && wide == 2;
+    fa.cull = (tree8 && p->cull >= 0) ? 1 : 0;
+    int drain_k = (tree8 && p->drain_k >= 0 && 7 * c->depth8 + 1 <= RT_DRAIN_STACK) ? (p->drain_k > 0 ? std::min(p->drain_k, 32) : 8) : 0;
+    if (cfg.work_counters && c->want_trace) drain_k = 0; // the per-warp timeline describes the per-lane kernel alone
     fa.refill_threshold = p->refill_threshold > 0 ? std::min(p->refill_threshold, 32) : 20;
 
     S.width = w; S.height = h; S.aov_mask = p->aov_mask; S.spp = p->spp; S.flags = p->frame_flags;
@@ -605,7 +626,7 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         Dev& D = c->devs[d];
         CK(c, cudaSetDevice(D.id));
         RtDeviceScene sc = c->scene_host_view;
-        sc.nodes = D.nodes; sc.nodes4 = D.nodes4; sc.tris = D.tris; sc.shade = D.shade;
+        sc.nodes = D.nodes; sc.nodes4 = D.nodes4; sc.nodes8 = D.nodes8; sc.tris = D.tris; sc.shade = D.shade;
         sc.mats = D.mats; sc.lights = D.lights; sc.leaf_cnt = D.leaf_cnt;
         RtFrameArgs f = fa;
         f.tile_list = D.tile_list; f.n_tiles = D.n_tiles;
@@ -630,6 +651,13 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         const int warps_needed = (D.n_tiles * (RT_TILE_PIXELS / 32) + (cf.block_threads / 32) - 1) / (cf.block_threads / 32);
         if (warps_needed < cf.grid) cf.grid = std::max(warps_needed, 1);
 
+        f.drain_k = 0; f.drain_queue = nullptr; f.drain_cap = 0;
+        f.drain_count = reinterpret_cast<unsigned*>(ctrl + 5); f.drain_next = reinterpret_cast<unsigned*>(ctrl + 6);
+        if (drain_k > 0) {
+            const size_t cap = (size_t)cf.grid * (cf.block_threads / 32) * (size_t)drain_k;
+            if ((rc = ensure(c, &D.drain_queue[slot], &D.drain_cap[slot], cap))) return rc;
+            f.drain_k = drain_k; f.drain_queue = D.drain_queue[slot]; f.drain_cap = (unsigned)cap;
+        }
         f.warp_trace = nullptr;
         if (cf.work_counters && c->want_trace) {
             const size_t nw = (size_t)cf.grid * (cf.block_threads / 32);
@@ -645,6 +673,10 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         e = (p->mode == RT_MODE_STRICT) ? rt_launch_strict(sc, f, cf, D.stream) : rt_launch_fast(sc, f, cf, D.stream);
         CK(c, e);
         launches++;
+        if (f.drain_k > 0) { // the paths the render kernel's warps handed off at the end of the chunk queue
+            CK(c, rt_launch_drain(sc, f, cf.work_counters, D.sm_count, D.stream));
+            launches++;
+        }
         CK(c, cudaEventRecord(D.ev1[slot], D.stream));
         // statistics -> pinned host memory on the second stream (this slot's control block is not touched again before
         // the slot has been waited on, so the next frame's kernel does not depend on this copy)
@@ -893,6 +925,19 @@ int rt_debug_set_tile_order(rt_ctx* c, const unsigned* tiles, int n)
     if (n != D.n_tiles) return fail(c, RT_ERR_INVALID, "rt_debug_set_tile_order: tile count differs from the current tile list");
     CK(c, cudaSetDevice(D.id));
     CK(c, cudaMemcpy(D.tile_list, tiles, (size_t)n * 4, cudaMemcpyHostToDevice));
+    return RT_OK;
+}
+
+int rt_debug_device_array(rt_ctx* c, int which, void* out, size_t cap_bytes, size_t* bytes_out)
+{
+    if (!c || !bytes_out || which < 0 || which > 7) return fail(c, RT_ERR_INVALID, "rt_debug_device_array: bad argument");
+    Dev& D = c->devs[0];
+    const void* src[8] = {D.nodes, D.nodes4, D.tris, D.shade, D.leaf_cnt, D.mats, D.lights, D.nodes8};
+    *bytes_out = D.bytes[which];
+    if (!out) return RT_OK;
+    if (cap_bytes < D.bytes[which]) return fail(c, RT_ERR_INVALID, "rt_debug_device_array: buffer too small");
+    CK(c, cudaSetDevice(D.id));
+    if (D.bytes[which]) CK(c, cudaMemcpy(out, src[which], D.bytes[which], cudaMemcpyDeviceToHost));
     return RT_OK;
 }
 

@@ -34,12 +34,12 @@ int build_wide8(const rt_bvh_node* bvh, uint32_t bvh_len, Wide8Tree& out)
     if (!bvh || !bvh_len) return RT_ERR_INVALID;
     auto is_inner = [&](uint32_t b) { return bvh[b].tr_len == 0 && bvh[b].idx != 0; };
     int32_t rf = 0, rc = 0;
-    if (!is_inner(0) || w8_small_subtree(bvh, 0, &rf, &rc)) {
-        // the whole tree is one leaf (a handful of triangles, or a depth-capped heap): one node with one child
+    if (!is_inner(0)) {
+        // the root itself is a leaf (<= 2 triangles): one node with one child
         W8Child c;
         for (int a = 0; a < 3; a++) { c.mn[a] = bvh[0].min[a]; c.mx[a] = bvh[0].max[a]; }
         c.bnode = 0; c.inner = 0;
-        if (!is_inner(0)) { rf = bvh[0].idx; rc = bvh[0].tr_len; }
+        rf = bvh[0].idx; rc = bvh[0].tr_len;
         const int slot = 0;
         const int32_t ref = w8_leaf_ref(rf, rc);
         out.words.resize(kWide8Words);

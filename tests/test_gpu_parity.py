@@ -67,7 +67,7 @@ def test_fast_vs_oracle(rt, gpu_scenes, oracle_scenes, manifest, scene, cam):
 
 
 @pytest.mark.parametrize("scene", SCENES)
-@pytest.mark.parametrize("traversal", [1, 2, 3])
+@pytest.mark.parametrize("traversal", [1, 2, 3, 4])
 def test_fast_traversal_variants_give_the_same_image(rt, gpu_scenes, oracle_scenes, scene, traversal):
     """RT_TRAVERSAL_PLAIN / SPECULATIVE / WIDE only change the visit order: depth and colour must agree with
     the oracle to the fast-build tolerances, and any two variants with each other on every non-tie pixel."""
