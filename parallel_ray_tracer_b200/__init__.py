@@ -128,7 +128,8 @@ def lib() -> C.CDLL:
     L.rt_create.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(i32), i32, C.POINTER(vp)]
     L.rt_debug_flatten_host.argtypes = [C.POINTER(rt_scene_desc), i32, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(i32)]
     L.rt_create_gpu.argtypes = [vp, i32, C.POINTER(i32), i32, i32, C.POINTER(vp), C.POINTER(rt_bvh_gpu_stats)]
-    L.rt_debug_device_array.argtypes = [vp, i32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    if hasattr(L, "rt_debug_device_array"):  # (absent from older builds loaded through RT_B200_LIB for A/B runs)
+        L.rt_debug_device_array.argtypes = [vp, i32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.rt_render.argtypes = [vp, C.POINTER(rt_render_params), C.POINTER(rt_timing)]
     L.rt_download.argtypes = [vp, vp, vp, vp, vp]
     L.rt_destroy.argtypes = [vp]; L.rt_destroy.restype = None

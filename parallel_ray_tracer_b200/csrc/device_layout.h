@@ -56,6 +56,9 @@ struct RtDeviceScene {
     const int*    leaf_cnt;
     int   n_lights;
     float amb[3];
+    // array lengths and an error word for the checked build (RT_DEBUG_BOUNDS, render_kernel.cuh); unused otherwise
+    unsigned n_tris, n_inner, n_nodes4, n_nodes8;
+    unsigned long long* err;
 };
 
 // A path handed from the per-lane render kernel to the cooperative drain kernel (render_kernel.cuh: drain_kernel): the

@@ -295,7 +295,7 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
     // ---- compressed 8-wide collapse (wide8.h): the fast build's default tree ----
     {
         Wide8Tree w8;
-        const int rc8 = build_wide8(d.bvh, nb, w8);
+        const int rc8 = build_wide8(d.bvh, nb, wide8_leaf_max(), w8);
         if (rc8) { err = "BVH child index out of range (8-wide collapse)"; return rc8; }
         out.nodes8.assign(w8.words.begin(), w8.words.end());
         out.depth8 = w8.depth;

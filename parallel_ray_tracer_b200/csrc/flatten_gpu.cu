@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -20,6 +21,10 @@
 #include "gpu_tree.h"
 #include "staged_copy.h"
 #include "wide8.h"
+
+#ifndef RT_W8_DEVICE_BUILD_DEFAULT
+#define RT_W8_DEVICE_BUILD_DEFAULT false /* until the device builder has run clean on the GPU box */
+#endif
 
 namespace {
 
@@ -159,25 +164,25 @@ __global__ void need4_kernel(int n4, const float4* __restrict__ nodes4, const un
 
 // ---- compressed 8-wide tree (wide8.h), level by level exactly as wide8.cpp builds it on the host ----
 // pass A: inner children per node of the level
-__global__ void w8_count_kernel(int n, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, int* __restrict__ n_inner)
+__global__ void w8_count_kernel(int n, int leaf_max, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, int* __restrict__ n_inner)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     rt::W8Child ch[8];
-    const int c = rt::w8_expand(bvh, level[i], ch);
+    const int c = rt::w8_expand(bvh, level[i], leaf_max, ch);
     int k = 0;
     for (int j = 0; j < c; j++) k += ch[j].inner;
     n_inner[i] = k;
 }
 // pass B: the next level's node list (inner children in slot order, the order their indices are assigned in)
-__global__ void w8_next_kernel(int n, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, const int* __restrict__ offset,
+__global__ void w8_next_kernel(int n, int leaf_max, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, const int* __restrict__ offset,
                                unsigned* __restrict__ next)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     rt::W8Child ch[8];
     int slot_of[8];
-    const int c = rt::w8_expand(bvh, level[i], ch);
+    const int c = rt::w8_expand(bvh, level[i], leaf_max, ch);
     rt::w8_assign_slots(ch, c, slot_of);
     int m = 0;
     for (int s = 0; s < 8; s++)
@@ -185,16 +190,25 @@ __global__ void w8_next_kernel(int n, const unsigned* __restrict__ level, const 
             if (slot_of[j] == s && ch[j].inner) next[offset[i] + m++] = (unsigned)ch[j].bnode;
 }
 // pass C: the records of the level
-__global__ void w8_encode_kernel(int n, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, const int* __restrict__ offset,
-                                 unsigned base, unsigned next_base, unsigned* __restrict__ words)
+__global__ void w8_encode_kernel(int n, int leaf_max, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, const int* __restrict__ offset,
+                                 unsigned base, unsigned next_base, unsigned* __restrict__ words, int* __restrict__ dbg_flag)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     rt::W8Child ch[8];
     int slot_of[8];
     int32_t ref_of[8];
-    const int c = rt::w8_expand(bvh, level[i], ch);
+    const int c = rt::w8_expand(bvh, level[i], leaf_max, ch);
     rt::w8_assign_slots(ch, c, slot_of);
+    {   // self-check: the slots must be a partial permutation of 0..7 (anything else would index outside the record)
+        unsigned seen = 0;
+        bool ok = c >= 1 && c <= 8;
+        for (int j = 0; ok && j < c; j++) {
+            if (slot_of[j] < 0 || slot_of[j] > 7 || ((seen >> slot_of[j]) & 1u)) ok = false;
+            else seen |= 1u << slot_of[j];
+        }
+        if (!ok) { atomicMax(dbg_flag, (int)level[i] + 1); return; }
+    }
     for (int j = 0; j < c; j++) ref_of[j] = ch[j].inner ? 0 : rt::w8_leaf_ref(ch[j].first, ch[j].cnt);
     int m = 0;
     for (int s = 0; s < 8; s++)
@@ -275,7 +289,19 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
     Buf nodes8;
     size_t n8 = 0;
     int depth8 = 0;
-    {
+    // RT_W8_DEVICE_BUILD=0 builds the 8-wide tree on the host from a copy of the device tree (wide8.cpp) and uploads it
+    const char* w8_env = std::getenv("RT_W8_DEVICE_BUILD");
+    const bool w8_on_device = w8_env ? std::atoi(w8_env) != 0 : RT_W8_DEVICE_BUILD_DEFAULT;
+    if (!w8_on_device) {
+        std::vector<rt_bvh_node> host_nodes((size_t)nn);
+        CKF(cudaDeviceSynchronize());
+        CKF(rt::staged_d2h(host_nodes.data(), t.nodes, (size_t)nn * sizeof(rt_bvh_node), 0));
+        rt::Wide8Tree w8;
+        if (rt::build_wide8(host_nodes.data(), (uint32_t)nn, rt::wide8_leaf_max(), w8)) { err = "flatten_gpu: 8-wide collapse failed"; return RT_ERR_INVALID; }
+        n8 = w8.n_nodes(); depth8 = w8.depth;
+        CKF(nodes8.alloc(n8 * 96));
+        CKF(rt::staged_h2d(nodes8.p, w8.words.data(), n8 * 96, 0));
+    } else {
         std::vector<Buf> lists, offs;   // per level: node list, exclusive scan of the inner-child counts
         std::vector<int> sizes;
         lists.reserve(72); offs.reserve(72);  // (Buf is not movable: no reallocation; at most 66 levels, checked below)
@@ -283,15 +309,19 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
         CKF(lists[0].alloc(4));
         CKF(cudaMemset(lists[0].p, 0, 4)); // level 0 = {reference node 0}
         sizes.push_back(1);
-        Buf cnt, tmp;
+        Buf tmp;
         size_t tmp_cap = 0;
+        const int leaf_max = rt::wide8_leaf_max();
+        const bool dbg = std::getenv("RT_SYNC_DEBUG") != nullptr; // name the failing kernel (no compute-sanitizer on the pool)
+#define CKL(what) do { if (dbg) { cudaError_t e__ = cudaDeviceSynchronize(); if (e__ != cudaSuccess) { err = std::string("flatten_gpu: ") + what + " (level " + std::to_string(lv) + "): " + cudaGetErrorString(e__); return RT_ERR_CUDA; } } } while (0)
         for (int lv = 0; sizes[lv] > 0; lv++) {
             if (lv > 64) { err = "flatten_gpu: 8-wide tree deeper than 64 levels"; return RT_ERR_INVALID; }
             const int m = sizes[lv];
             Buf c2;
             CKF(c2.alloc(((size_t)m + 1) * 4));
             CKF(cudaMemset(c2.p, 0, ((size_t)m + 1) * 4));
-            w8_count_kernel<<<(m + 127) / 128, 128>>>(m, lists[lv].as<unsigned>(), t.nodes, c2.as<int>());
+            w8_count_kernel<<<(m + 127) / 128, 128>>>(m, leaf_max, lists[lv].as<unsigned>(), t.nodes, c2.as<int>());
+            CKL("w8_count_kernel");
             offs.emplace_back();
             CKF(offs[lv].alloc(((size_t)m + 1) * 4));
             size_t need = 0;
@@ -302,8 +332,9 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
             CKF(cudaMemcpy(&total, offs[lv].as<int>() + m, 4, cudaMemcpyDeviceToHost));
             lists.emplace_back();
             CKF(lists[lv + 1].alloc((size_t)std::max(total, 1) * 4));
-            if (total > 0) w8_next_kernel<<<(m + 127) / 128, 128>>>(m, lists[lv].as<unsigned>(), t.nodes, offs[lv].as<int>(), lists[lv + 1].as<unsigned>());
+            if (total > 0) w8_next_kernel<<<(m + 127) / 128, 128>>>(m, leaf_max, lists[lv].as<unsigned>(), t.nodes, offs[lv].as<int>(), lists[lv + 1].as<unsigned>());
             CKF(cudaGetLastError());
+            CKL("w8_next_kernel");
             sizes.push_back(total);
             n8 += (size_t)m;
             depth8++;
@@ -312,13 +343,17 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
         size_t base = 0;
         for (int lv = 0; lv < depth8; lv++) {
             const int m = sizes[lv];
-            w8_encode_kernel<<<(m + 127) / 128, 128>>>(m, lists[lv].as<unsigned>(), t.nodes, offs[lv].as<int>(), (unsigned)base, (unsigned)(base + (size_t)m),
-                                                       nodes8.as<unsigned>());
+            w8_encode_kernel<<<(m + 127) / 128, 128>>>(m, leaf_max, lists[lv].as<unsigned>(), t.nodes, offs[lv].as<int>(), (unsigned)base, (unsigned)(base + (size_t)m),
+                                                       nodes8.as<unsigned>(), &flags.as<FlatFlags>()->bad_leaf);
+            CKL("w8_encode_kernel");
             base += (size_t)m;
         }
         CKF(cudaGetLastError());
+#undef CKL
     }
     CKF(cudaDeviceSynchronize());
+    CKF(cudaMemcpy(&fl, flags.p, sizeof fl, cudaMemcpyDeviceToHost));
+    if (fl.bad_leaf) { err = "flatten_gpu: 8-wide slot assignment failed at reference node " + std::to_string(fl.bad_leaf - 1); return RT_ERR_STATE; }
     out.nodes = nodes.take<float4>(); out.nodes4 = nodes4.take<float4>(); out.tris = tris.take<float4>(); out.shade = shade.take<float4>();
     out.leaf_cnt = fl.need_leaf_cnt ? leaf_cnt.take<int>() : nullptr;
     out.nodes8 = nodes8.take<uint4>(); out.n_nodes8 = n8; out.depth8 = depth8;

@@ -612,7 +612,7 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
             }
             CK(c, cudaEventRecord(D.ev1[slot], D.stream));
             CK(c, cudaStreamWaitEvent(D.aux, D.ev1[slot], 0));
-            CK(c, cudaMemcpyAsync(D.ctrl_host + 8 * slot, ctrl, 32, cudaMemcpyDeviceToHost, D.aux));
+            CK(c, cudaMemcpyAsync(D.ctrl_host + 8 * slot, ctrl, 64, cudaMemcpyDeviceToHost, D.aux));
             CK(c, cudaEventRecord(D.ev_done[slot], D.aux));
         }
         S.launches = 1;
@@ -628,6 +628,9 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         RtDeviceScene sc = c->scene_host_view;
         sc.nodes = D.nodes; sc.nodes4 = D.nodes4; sc.nodes8 = D.nodes8; sc.tris = D.tris; sc.shade = D.shade;
         sc.mats = D.mats; sc.lights = D.lights; sc.leaf_cnt = D.leaf_cnt;
+        sc.n_inner = (unsigned)(D.bytes[0] / 64); sc.n_nodes4 = (unsigned)(D.bytes[1] / 128); sc.n_tris = (unsigned)(D.bytes[2] / 64);
+        sc.n_nodes8 = (unsigned)(D.bytes[7] / 96);
+        sc.err = D.ctrl + RT_CTRL_WORDS * slot + 7; // written by the checked build only (RT_DEBUG_BOUNDS)
         RtFrameArgs f = fa;
         f.tile_list = D.tile_list; f.n_tiles = D.n_tiles;
         unsigned long long* const ctrl = D.ctrl + RT_CTRL_WORDS * slot;
@@ -681,7 +684,7 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         // statistics -> pinned host memory on the second stream (this slot's control block is not touched again before
         // the slot has been waited on, so the next frame's kernel does not depend on this copy)
         CK(c, cudaStreamWaitEvent(D.aux, D.ev1[slot], 0));
-        CK(c, cudaMemcpyAsync(D.ctrl_host + 8 * slot, ctrl, 32, cudaMemcpyDeviceToHost, D.aux));
+        CK(c, cudaMemcpyAsync(D.ctrl_host + 8 * slot, ctrl, 64, cudaMemcpyDeviceToHost, D.aux));
         CK(c, cudaEventRecord(D.ev_done[slot], D.aux));
     }
     S.render_pending = true;
@@ -769,6 +772,10 @@ static int finish_frame(rt_ctx* c, int slot, rt_timing* tm)
             t.rays_shadow += st[1];
             t.inner_visits += st[2];
             t.tri_tests += st[3];
+            if (st[7]) { // checked build: an index left its array (render_kernel.cuh: RT_BCHECK codes)
+                S.render_pending = false;
+                return fail(c, RT_ERR_STATE, "RT_DEBUG_BOUNDS: check " + std::to_string(st[7]) + " failed on device " + std::to_string(D.id));
+            }
         }
         t.gather_ms = S.gather_ms;
         t.total_ms = kmax + S.gather_ms;

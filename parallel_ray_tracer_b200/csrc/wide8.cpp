@@ -27,7 +27,14 @@ void par_for(size_t count, F f)
 }
 } // namespace
 
-int build_wide8(const rt_bvh_node* bvh, uint32_t bvh_len, Wide8Tree& out)
+int wide8_leaf_max()
+{
+    const char* e = std::getenv("RT_W8_LEAF_MAX");
+    int v = e ? std::atoi(e) : kWide8LeafMaxDefault;
+    return v < 2 ? 2 : (v > RT_W8_LEAF_CAP ? RT_W8_LEAF_CAP : v);
+}
+
+int build_wide8(const rt_bvh_node* bvh, uint32_t bvh_len, int leaf_max, Wide8Tree& out)
 {
     out.words.clear();
     out.depth = 0;
@@ -61,7 +68,7 @@ int build_wide8(const rt_bvh_node* bvh, uint32_t bvh_len, Wide8Tree& out)
             for (size_t i = lo; i < hi; i++) {
                 const uint32_t r = level[i];
                 if ((uint64_t)bvh[r].idx + 1 >= bvh_len || bvh[r].idx < 1) { bad.store(1); continue; }
-                const int c = w8_expand(bvh, r, ch);
+                const int c = w8_expand(bvh, r, leaf_max, ch);
                 uint32_t k = 0;
                 for (int j = 0; j < c; j++) k += (uint32_t)ch[j].inner;
                 n_inner[i] = k;
@@ -77,7 +84,7 @@ int build_wide8(const rt_bvh_node* bvh, uint32_t bvh_len, Wide8Tree& out)
             int slot_of[8];
             int32_t ref_of[8];
             for (size_t i = lo; i < hi; i++) {
-                const int c = w8_expand(bvh, level[i], ch);
+                const int c = w8_expand(bvh, level[i], leaf_max, ch);
                 w8_assign_slots(ch, c, slot_of);
                 // inner children are numbered in SLOT order (what a kernel could recompute from the slot alone)
                 int order[8], m = 0;

@@ -43,17 +43,15 @@ constexpr int kWide8StackMax = 40;    // group-stack entries a kernel provides (
 struct W8Child {
     float mn[3], mx[3];
     int32_t bnode; // reference node index
-    int32_t inner; // 1: becomes an 8-wide node, 0: leaf (a reference leaf, or a whole reference subtree of <= kWide8LeafMax triangles)
+    int32_t inner; // 1: becomes an 8-wide node, 0: leaf (a reference leaf, or a whole reference subtree of <= leaf_max triangles)
     int32_t first, cnt; // leaf: triangle slots [first, first + cnt)
 };
 
 // Reference subtrees of at most this many triangles become ONE leaf of the 8-wide tree (their slots are contiguous:
 // bvh_split partitions tri_idx in place, cpu/src/bvh.c:244-259).  Testing 3-4 triangles costs less than visiting an
 // 8-wide node whose slots would be three quarters empty; the image cannot change (the triangle test is the hit test).
-#ifndef RT_W8_LEAF_MAX
-#define RT_W8_LEAF_MAX 4
-#endif
-constexpr int kWide8LeafMax = RT_W8_LEAF_MAX;
+#define RT_W8_LEAF_CAP 8                 /* largest value of the knob */
+constexpr int kWide8LeafMaxDefault = 4;  /* rt_create default; RT_W8_LEAF_MAX in the environment overrides it (experiments) */
 
 // surface area of a box, double (only used to rank the children of ONE node against each other)
 RT_W8_HD inline double w8_area(const float* mn, const float* mx)
@@ -64,10 +62,10 @@ RT_W8_HD inline double w8_area(const float* mn, const float* mx)
 
 RT_W8_HD inline bool w8_is_inner(const rt_bvh_node& nd) { return nd.tr_len == 0 && nd.idx != 0; }
 
-// Triangle slots below reference node b, if there are at most kWide8LeafMax of them (bounded walk, left to right).
-RT_W8_HD inline bool w8_small_subtree(const rt_bvh_node* bvh, uint32_t b, int32_t* first, int32_t* cnt)
+// Triangle slots below reference node b, if there are at most leaf_max (<= RT_W8_LEAF_CAP) of them (bounded walk, left to right).
+RT_W8_HD inline bool w8_small_subtree(const rt_bvh_node* bvh, uint32_t b, int leaf_max, int32_t* first, int32_t* cnt)
 {
-    uint32_t stack[2 * RT_W8_LEAF_MAX + 34];
+    uint32_t stack[2 * RT_W8_LEAF_CAP + 34];
     int sp = 0, total = 0;
     int32_t f = -1;
     stack[sp++] = b;
@@ -80,7 +78,7 @@ RT_W8_HD inline bool w8_small_subtree(const rt_bvh_node* bvh, uint32_t b, int32_
         } else if (nd.tr_len > 0) {
             if (f < 0) f = nd.idx;
             total += nd.tr_len;
-            if (total > kWide8LeafMax) return false;
+            if (total > leaf_max) return false;
         }
     }
     *first = f < 0 ? 0 : f;
@@ -96,7 +94,7 @@ RT_W8_HD inline int32_t w8_leaf_ref(int32_t first, int32_t cnt)
 
 // The frontier of reference node `root` (an inner node): up to 8 children, in the order the expansion leaves them
 // (left to right in the reference tree).  Empty leaves of the reference tree (tr_len == 0 && idx == 0) are dropped.
-RT_W8_HD inline int w8_expand(const rt_bvh_node* bvh, uint32_t root, W8Child* out)
+RT_W8_HD inline int w8_expand(const rt_bvh_node* bvh, uint32_t root, int leaf_max, W8Child* out)
 {
     int n = 0;
     auto put = [&](int at, uint32_t b) {
@@ -106,7 +104,7 @@ RT_W8_HD inline int w8_expand(const rt_bvh_node* bvh, uint32_t root, W8Child* ou
         c.bnode = (int32_t)b;
         c.first = nd.idx; c.cnt = nd.tr_len;
         c.inner = 0;
-        if (w8_is_inner(nd)) c.inner = w8_small_subtree(bvh, b, &c.first, &c.cnt) ? 0 : 1;
+        if (w8_is_inner(nd)) c.inner = w8_small_subtree(bvh, b, leaf_max, &c.first, &c.cnt) ? 0 : 1;
     };
     auto empty = [&](uint32_t b) { return bvh[b].tr_len == 0 && bvh[b].idx == 0; };
     const uint32_t l = (uint32_t)bvh[root].idx;
@@ -280,6 +278,7 @@ struct Wide8Tree {
     int depth = 0;               // levels of 8-wide nodes (a ray's group stack needs depth + 1 entries)
     size_t n_nodes() const { return words.size() / kWide8Words; }
 };
-int build_wide8(const rt_bvh_node* bvh, uint32_t bvh_len, Wide8Tree& out);
+int build_wide8(const rt_bvh_node* bvh, uint32_t bvh_len, int leaf_max, Wide8Tree& out);
+int wide8_leaf_max(); // the knob: kWide8LeafMaxDefault or RT_W8_LEAF_MAX from the environment, clamped to [2, RT_W8_LEAF_CAP]
 
 } // namespace rt

@@ -91,6 +91,7 @@ def kernel_box_hits(w, o, d, tmax):
     """The kernels' test of the eight children of one node (render_kernel.cuh: wide8_visit), float32 op for op:
     returns the hit mask in SLOT order."""
     f32 = np.float32
+    d = np.where(np.abs(d) < f32(1e-30), np.copysign(f32(1e-30), d), d).astype(f32)   # ray_begin: zero components for the box test
     idv = (f32(1.0) / d).astype(f32)
     ob = (-o * idv).astype(f32)
     p = w[0:3].view(np.float32)
@@ -122,7 +123,8 @@ def kernel_box_hits(w, o, d, tmax):
 
 def walk(n8, leaf_cnt, tris, o, d, orc):
     """Closest hit through the 8-wide tree in octant order; triangles tested with the oracle's hit_triangle."""
-    octant = (1 if d[0] < 0 else 0) | (2 if d[1] < 0 else 0) | (4 if d[2] < 0 else 0)
+    ds = np.where(np.abs(d) < np.float32(1e-30), np.copysign(np.float32(1e-30), d), d)
+    octant = (1 if ds[0] < 0 else 0) | (2 if ds[1] < 0 else 0) | (4 if ds[2] < 0 else 0)
     best_t, best = np.float32(3.4028234663852886e38), -1
     stack = [0]
     visited = 0
