@@ -189,10 +189,10 @@ typedef struct rt_render_params {
     int32_t   traversal;        /* RT_TRAVERSAL_* (fast mode only; strict always walks the reference order) */
     int32_t   frame_flags;      /* RT_FRAME_* */
     int32_t   frame_slot;       /* which of the context's RT_FRAME_SLOTS device frames to render into (frame sequences) */
-    /* fast build on the compressed 8-wide tree (0 = library default, < 0 = off): */
+    /* fast build on the compressed 8-wide tree (RT_TRAVERSAL_WIDE8), both off unless > 0: */
     int32_t   drain_k;          /* once the chunk queue is empty, a warp left with <= drain_k live pixels hands them to the
-                                   cooperative drain kernel (eight lanes per ray); default 8 */
-    int32_t   cull;             /* test every 8x4-pixel chunk's ray pyramid against the top of the tree first; default on */
+                                   cooperative drain kernel (eight lanes per ray) */
+    int32_t   cull;             /* test every 8x4-pixel chunk's ray pyramid against the top of the tree before tracing it */
 } rt_render_params;
 
 typedef struct rt_timing {

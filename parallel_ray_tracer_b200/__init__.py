@@ -97,6 +97,12 @@ def build(verbose: bool = False) -> Path:
         print(r.stdout[-4000:], r.stderr[-4000:])
     if r.returncode != 0:
         raise RuntimeError("building librt_b200.so failed")
+    # the checked twin (RT_DEBUG_BOUNDS, tests/test_gpu_checked.py)
+    r = subprocess.run(["make", "-C", str(PKG_DIR / "csrc"), "-j", str(os.cpu_count() or 4), "checked"], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode != 0:
+        raise RuntimeError("building librt_b200_checked.so failed")
     return LIB_PATH
 
 

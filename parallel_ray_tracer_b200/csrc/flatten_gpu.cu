@@ -23,7 +23,7 @@
 #include "wide8.h"
 
 #ifndef RT_W8_DEVICE_BUILD_DEFAULT
-#define RT_W8_DEVICE_BUILD_DEFAULT false /* until the device builder has run clean on the GPU box */
+#define RT_W8_DEVICE_BUILD_DEFAULT true
 #endif
 
 namespace {
@@ -174,9 +174,10 @@ __global__ void w8_count_kernel(int n, int leaf_max, const unsigned* __restrict_
     for (int j = 0; j < c; j++) k += ch[j].inner;
     n_inner[i] = k;
 }
-// pass B: the next level's node list (inner children in slot order, the order their indices are assigned in)
-__global__ void w8_next_kernel(int n, int leaf_max, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, const int* __restrict__ offset,
-                               unsigned* __restrict__ next)
+// pass B: the next level's node list (inner children in slot order, the order their indices are assigned in) and the
+// level's plan: per (node, slot) the reference node whose box the slot holds (-1 = empty) and the slot's final reference
+__global__ void w8_plan_kernel(int n, int leaf_max, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, const int* __restrict__ offset,
+                               unsigned next_base, unsigned* __restrict__ next, int* __restrict__ plan_node, int* __restrict__ plan_ref)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -184,41 +185,56 @@ __global__ void w8_next_kernel(int n, int leaf_max, const unsigned* __restrict__
     int slot_of[8];
     const int c = rt::w8_expand(bvh, level[i], leaf_max, ch);
     rt::w8_assign_slots(ch, c, slot_of);
+    for (int s = 0; s < 8; s++) { plan_node[8 * (size_t)i + s] = -1; plan_ref[8 * (size_t)i + s] = RT_REF_NONE; }
     int m = 0;
     for (int s = 0; s < 8; s++)
         for (int j = 0; j < c; j++)
-            if (slot_of[j] == s && ch[j].inner) next[offset[i] + m++] = (unsigned)ch[j].bnode;
+            if (slot_of[j] == s) {
+                plan_node[8 * (size_t)i + s] = ch[j].bnode;
+                if (ch[j].inner) {
+                    plan_ref[8 * (size_t)i + s] = (int)(next_base + (unsigned)offset[i] + (unsigned)m);
+                    next[offset[i] + m] = (unsigned)ch[j].bnode;
+                    m++;
+                } else plan_ref[8 * (size_t)i + s] = rt::w8_leaf_ref(ch[j].first, ch[j].cnt);
+            }
 }
-// pass C: the records of the level
-__global__ void w8_encode_kernel(int n, int leaf_max, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, const int* __restrict__ offset,
-                                 unsigned base, unsigned next_base, unsigned* __restrict__ words, int* __restrict__ dbg_flag)
+// pass C: the records of the level, one thread per (node, slot): the node's grid from the union of its children's boxes
+// (recomputed by each of the eight threads), the slot's own six bytes and reference, the header by slot 0
+__global__ void w8_encode_kernel(int n, const rt_bvh_node* __restrict__ bvh, const int* __restrict__ plan_node, const int* __restrict__ plan_ref,
+                                 unsigned base, unsigned* __restrict__ words)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = tid >> 3, slot = tid & 7;
     if (i >= n) return;
-    rt::W8Child ch[8];
-    int slot_of[8];
-    int32_t ref_of[8];
-    const int c = rt::w8_expand(bvh, level[i], leaf_max, ch);
-    rt::w8_assign_slots(ch, c, slot_of);
-    {   // self-check: the slots must be a partial permutation of 0..7 (anything else would index outside the record)
-        unsigned seen = 0;
-        bool ok = c >= 1 && c <= 8;
-        for (int j = 0; ok && j < c; j++) {
-            if (slot_of[j] < 0 || slot_of[j] > 7 || ((seen >> slot_of[j]) & 1u)) ok = false;
-            else seen |= 1u << slot_of[j];
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    int cnt = 0;
+    for (int s = 0; s < 8; s++) {
+        const int b = plan_node[8 * (size_t)i + s];
+        if (b < 0) continue;
+        const rt_bvh_node& nd = bvh[b];
+        for (int a = 0; a < 3; a++) {
+            if (!cnt || nd.min[a] < lo[a]) lo[a] = nd.min[a];
+            if (!cnt || nd.max[a] > hi[a]) hi[a] = nd.max[a];
         }
-        if (!ok) { atomicMax(dbg_flag, (int)level[i] + 1); return; }
+        cnt++;
     }
-    for (int j = 0; j < c; j++) ref_of[j] = ch[j].inner ? 0 : rt::w8_leaf_ref(ch[j].first, ch[j].cnt);
-    int m = 0;
-    for (int s = 0; s < 8; s++)
-        for (int j = 0; j < c; j++)
-            if (slot_of[j] == s && ch[j].inner) ref_of[j] = (int32_t)(next_base + (unsigned)offset[i] + (unsigned)m++);
-    uint32_t w[rt::kWide8Words];
-    rt::w8_encode(ch, c, slot_of, ref_of, w);
-    uint4* o = reinterpret_cast<uint4*>(words + (size_t)(base + (unsigned)i) * rt::kWide8Words);
-#pragma unroll
-    for (int k = 0; k < 6; k++) o[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+    int e[3];
+    float p[3];
+    for (int a = 0; a < 3; a++) rt::w8_node_axis(lo[a], hi[a], &e[a], &p[a]);
+    unsigned* w = words + (size_t)(base + (unsigned)i) * rt::kWide8Words;
+    unsigned char* q = reinterpret_cast<unsigned char*>(w + 4);
+    const int mine = plan_node[8 * (size_t)i + slot];
+    for (int a = 0; a < 3; a++) {
+        unsigned char ql = 255, qh = 0; // empty slot: inverted, never hit
+        if (mine >= 0) rt::w8_quantize(bvh[mine].min[a], bvh[mine].max[a], p[a], e[a], &ql, &qh);
+        q[8 * a + slot] = ql;
+        q[24 + 8 * a + slot] = qh;
+    }
+    w[16 + slot] = (unsigned)plan_ref[8 * (size_t)i + slot];
+    if (slot == 0) {
+        w[0] = __float_as_uint(p[0]); w[1] = __float_as_uint(p[1]); w[2] = __float_as_uint(p[2]);
+        w[3] = rt::w8_header_word(e, cnt);
+    }
 }
 
 struct Buf {
@@ -302,9 +318,9 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
         CKF(nodes8.alloc(n8 * 96));
         CKF(rt::staged_h2d(nodes8.p, w8.words.data(), n8 * 96, 0));
     } else {
-        std::vector<Buf> lists, offs;   // per level: node list, exclusive scan of the inner-child counts
+        std::vector<Buf> lists, plan_nodes, plan_refs;   // per level: node list, (node, slot) plan
         std::vector<int> sizes;
-        lists.reserve(72); offs.reserve(72);  // (Buf is not movable: no reallocation; at most 66 levels, checked below)
+        lists.reserve(72); plan_nodes.reserve(72); plan_refs.reserve(72); // (Buf is not movable: no reallocation; <= 66 levels, checked below)
         lists.emplace_back();
         CKF(lists[0].alloc(4));
         CKF(cudaMemset(lists[0].p, 0, 4)); // level 0 = {reference node 0}
@@ -314,28 +330,33 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
         const int leaf_max = rt::wide8_leaf_max();
         const bool dbg = std::getenv("RT_SYNC_DEBUG") != nullptr; // name the failing kernel (no compute-sanitizer on the pool)
 #define CKL(what) do { if (dbg) { cudaError_t e__ = cudaDeviceSynchronize(); if (e__ != cudaSuccess) { err = std::string("flatten_gpu: ") + what + " (level " + std::to_string(lv) + "): " + cudaGetErrorString(e__); return RT_ERR_CUDA; } } } while (0)
+        size_t done = 0; // nodes of the levels before this one
         for (int lv = 0; sizes[lv] > 0; lv++) {
             if (lv > 64) { err = "flatten_gpu: 8-wide tree deeper than 64 levels"; return RT_ERR_INVALID; }
             const int m = sizes[lv];
-            Buf c2;
+            Buf c2, off;
             CKF(c2.alloc(((size_t)m + 1) * 4));
             CKF(cudaMemset(c2.p, 0, ((size_t)m + 1) * 4));
             w8_count_kernel<<<(m + 127) / 128, 128>>>(m, leaf_max, lists[lv].as<unsigned>(), t.nodes, c2.as<int>());
             CKL("w8_count_kernel");
-            offs.emplace_back();
-            CKF(offs[lv].alloc(((size_t)m + 1) * 4));
+            CKF(off.alloc(((size_t)m + 1) * 4));
             size_t need = 0;
-            CKF(cub::DeviceScan::ExclusiveSum(nullptr, need, c2.as<int>(), offs[lv].as<int>(), m + 1));
+            CKF(cub::DeviceScan::ExclusiveSum(nullptr, need, c2.as<int>(), off.as<int>(), m + 1));
             if (need > tmp_cap) { cudaFree(tmp.p); tmp.p = nullptr; CKF(tmp.alloc(need)); tmp_cap = need; }
-            CKF(cub::DeviceScan::ExclusiveSum(tmp.p, need, c2.as<int>(), offs[lv].as<int>(), m + 1));
+            CKF(cub::DeviceScan::ExclusiveSum(tmp.p, need, c2.as<int>(), off.as<int>(), m + 1));
             int total = 0;
-            CKF(cudaMemcpy(&total, offs[lv].as<int>() + m, 4, cudaMemcpyDeviceToHost));
-            lists.emplace_back();
+            CKF(cudaMemcpy(&total, off.as<int>() + m, 4, cudaMemcpyDeviceToHost));
+            lists.emplace_back(); plan_nodes.emplace_back(); plan_refs.emplace_back();
             CKF(lists[lv + 1].alloc((size_t)std::max(total, 1) * 4));
-            if (total > 0) w8_next_kernel<<<(m + 127) / 128, 128>>>(m, leaf_max, lists[lv].as<unsigned>(), t.nodes, offs[lv].as<int>(), lists[lv + 1].as<unsigned>());
+            CKF(plan_nodes[lv].alloc((size_t)m * 32));
+            CKF(plan_refs[lv].alloc((size_t)m * 32));
+            w8_plan_kernel<<<(m + 127) / 128, 128>>>(m, leaf_max, lists[lv].as<unsigned>(), t.nodes, off.as<int>(), (unsigned)(done + (size_t)m),
+                                                     lists[lv + 1].as<unsigned>(), plan_nodes[lv].as<int>(), plan_refs[lv].as<int>());
             CKF(cudaGetLastError());
-            CKL("w8_next_kernel");
+            CKL("w8_plan_kernel");
+            CKF(cudaDeviceSynchronize()); // (c2 / off are freed at the end of the iteration)
             sizes.push_back(total);
+            done += (size_t)m;
             n8 += (size_t)m;
             depth8++;
         }
@@ -343,8 +364,7 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
         size_t base = 0;
         for (int lv = 0; lv < depth8; lv++) {
             const int m = sizes[lv];
-            w8_encode_kernel<<<(m + 127) / 128, 128>>>(m, leaf_max, lists[lv].as<unsigned>(), t.nodes, offs[lv].as<int>(), (unsigned)base, (unsigned)(base + (size_t)m),
-                                                       nodes8.as<unsigned>(), &flags.as<FlatFlags>()->bad_leaf);
+            w8_encode_kernel<<<(8 * m + 127) / 128, 128>>>(m, t.nodes, plan_nodes[lv].as<int>(), plan_refs[lv].as<int>(), (unsigned)base, nodes8.as<unsigned>());
             CKL("w8_encode_kernel");
             base += (size_t)m;
         }
@@ -352,8 +372,7 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
 #undef CKL
     }
     CKF(cudaDeviceSynchronize());
-    CKF(cudaMemcpy(&fl, flags.p, sizeof fl, cudaMemcpyDeviceToHost));
-    if (fl.bad_leaf) { err = "flatten_gpu: 8-wide slot assignment failed at reference node " + std::to_string(fl.bad_leaf - 1); return RT_ERR_STATE; }
+
     out.nodes = nodes.take<float4>(); out.nodes4 = nodes4.take<float4>(); out.tris = tris.take<float4>(); out.shade = shade.take<float4>();
     out.leaf_cnt = fl.need_leaf_cnt ? leaf_cnt.take<int>() : nullptr;
     out.nodes8 = nodes8.take<uint4>(); out.n_nodes8 = n8; out.depth8 = depth8;

@@ -581,10 +581,11 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
     cfg.work_counters = (p->aov_mask & RT_AOV_WORK) != 0;
     cfg.speculative = p->traversal != RT_TRAVERSAL_PLAIN;
     cfg.wide = wide;
-    // tail of the frame on the compressed tree: chunk culling and the cooperative drain kernel (defaults on; < 0 = off)
+    // on the compressed tree: chunk culling and the cooperative drain kernel, both opt-in (measured neutral / slower on the
+    // shipped scenes, profiles/r02_notes.md)
     const bool tree8 = p->mode == RT_MODE_FAST && wide == 2;
-    fa.cull = (tree8 && p->cull >= 0) ? 1 : 0;
-    int drain_k = (tree8 && p->drain_k >= 0 && 7 * c->depth8 + 1 <= RT_DRAIN_STACK) ? (p->drain_k > 0 ? std::min(p->drain_k, 32) : 8) : 0;
+    fa.cull = (tree8 && p->cull > 0) ? 1 : 0;
+    int drain_k = (tree8 && p->drain_k > 0 && 7 * c->depth8 + 1 <= RT_DRAIN_STACK) ? std::min(p->drain_k, 32) : 0;
     if (cfg.work_counters && c->want_trace) drain_k = 0; // the per-warp timeline describes the per-lane kernel alone
     fa.refill_threshold = p->refill_threshold > 0 ? std::min(p->refill_threshold, 32) : 20;
 

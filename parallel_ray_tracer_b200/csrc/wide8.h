@@ -220,6 +220,32 @@ RT_W8_HD inline void w8_axis_grid(float lo, float hi, double amax, int* e_out, f
     }
 }
 
+// One axis of one child on the node's grid (origin p, step 2^e): outward-rounded bytes with the 1/16-step margin.
+RT_W8_HD inline void w8_quantize(float cmn, float cmx, float p, int e, unsigned char* qlo, unsigned char* qhi)
+{
+    const double st = w8_pow2(e);
+    const double ql = ((double)cmn - (double)p) / st - 0.0625;
+    const double qh = ((double)cmx - (double)p) / st + 0.0625;
+    long long il = (long long)ql; if ((double)il > ql) il--;   // floor
+    long long ih = (long long)qh; if ((double)ih < qh) ih++;   // ceil
+    if (il < 0) il = 0;
+    if (il > 255) il = 255;
+    if (ih > 255) ih = 255;
+    if (ih < 0) ih = 0;
+    *qlo = (unsigned char)il;
+    *qhi = (unsigned char)ih;
+}
+// The grid of one axis of a node whose children span [lo, hi] on it
+RT_W8_HD inline void w8_node_axis(float lo, float hi, int* e, float* p)
+{
+    const double al = lo < 0 ? -(double)lo : (double)lo, ah = hi < 0 ? -(double)hi : (double)hi;
+    w8_axis_grid(lo, hi, al > ah ? al : ah, e, p);
+}
+RT_W8_HD inline uint32_t w8_header_word(const int* e, int n)
+{
+    return (uint32_t)(e[0] - 7 + 127) | ((uint32_t)(e[1] - 7 + 127) << 8) | ((uint32_t)(e[2] - 7 + 127) << 16) | ((uint32_t)n << 24);
+}
+
 // Encode one node.  kids[0..n) with their slots; ref_of[i] = device reference of child i.  `w` receives 24 words.
 RT_W8_HD inline void w8_encode(const W8Child* ch, int n, const int* slot_of, const int32_t* ref_of, uint32_t* w)
 {
@@ -232,37 +258,21 @@ RT_W8_HD inline void w8_encode(const W8Child* ch, int n, const int* slot_of, con
         }
     int e[3];
     float p[3];
-    for (int a = 0; a < 3; a++) {
-        const double al = lo[a] < 0 ? -(double)lo[a] : (double)lo[a], ah = hi[a] < 0 ? -(double)hi[a] : (double)hi[a];
-        w8_axis_grid(lo[a], hi[a], al > ah ? al : ah, &e[a], &p[a]);
-    }
+    for (int a = 0; a < 3; a++) w8_node_axis(lo[a], hi[a], &e[a], &p[a]);
     for (int k = 0; k < kWide8Words; k++) w[k] = 0;
     for (int a = 0; a < 3; a++) {
         union { float f; uint32_t u; } v;
         v.f = p[a];
         w[a] = v.u;
     }
-    // E = biased exponent of s/128
-    w[3] = (uint32_t)(e[0] - 7 + 127) | ((uint32_t)(e[1] - 7 + 127) << 8) | ((uint32_t)(e[2] - 7 + 127) << 16) | ((uint32_t)n << 24);
+    w[3] = w8_header_word(e, n); // E = biased exponent of s/128 per axis, child count
     unsigned char qlo[3][8], qhi[3][8];
     for (int a = 0; a < 3; a++)
         for (int s = 0; s < 8; s++) { qlo[a][s] = 255; qhi[a][s] = 0; } // empty slot: inverted, never hit
     for (int s = 0; s < 8; s++) w[16 + s] = 0x80000000u;               // RT_REF_NONE
     for (int i = 0; i < n; i++) {
         const int s = slot_of[i];
-        for (int a = 0; a < 3; a++) {
-            const double st = w8_pow2(e[a]);
-            double ql = ((double)ch[i].mn[a] - (double)p[a]) / st - 0.0625;
-            double qh = ((double)ch[i].mx[a] - (double)p[a]) / st + 0.0625;
-            long long il = (long long)ql; if ((double)il > ql) il--;   // floor
-            long long ih = (long long)qh; if ((double)ih < qh) ih++;   // ceil
-            if (il < 0) il = 0;
-            if (il > 255) il = 255;
-            if (ih > 255) ih = 255;
-            if (ih < 0) ih = 0;
-            qlo[a][s] = (unsigned char)il;
-            qhi[a][s] = (unsigned char)ih;
-        }
+        for (int a = 0; a < 3; a++) w8_quantize(ch[i].mn[a], ch[i].mx[a], p[a], e[a], &qlo[a][s], &qhi[a][s]);
         w[16 + s] = (uint32_t)ref_of[i];
     }
     for (int a = 0; a < 3; a++)

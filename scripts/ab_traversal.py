@@ -16,8 +16,7 @@ CASES = [("car_only", 1920, 1080), ("car_boxed", 1920, 1080), ("car_boxed", 3840
 
 def main():
     frames = int(sys.argv[1]) if len(sys.argv) > 1 else 30
-    variants = [tuple(int(x) for x in v.split(":")) for v in sys.argv[2:]] or [(2, 8), (3, 6), (4, 5, -1, -1), (4, 6, -1, -1), (4, 7, -1, -1),
-                                                                                (4, 6, 0, -1), (4, 6, 0, 4), (4, 6, 0, 8), (4, 6, 0, 16), (4, 5, 0, 8), (4, 7, 0, 8)]
+    variants = [tuple(int(x) for x in v.split(":")) for v in sys.argv[2:]] or [(2, 8), (3, 6), (4, 5), (4, 6), (4, 7), (4, 6, 1, 0), (4, 6, 1, 2), (4, 6, 1, 8)]
     variants = [tuple(v) + (0, 0)[len(v) - 2:] for v in variants]
     for scene, w, h in CASES:
         sc = rt.Scene.load_rtsc(ROOT / "tests" / "golden" / "scenes" / f"{scene}.rtsc").build_bvh(6)

@@ -36,11 +36,13 @@ def test_b200_arm_line(rt):
     assert BASE_KEYS <= set(d) and d["metric"] == "Mrays/s" and d["n_gpus"] == 1 and d["steps"] == 4 and d["warmup"] >= 3
     assert d["config"]["workload"] == "car_only_1080p" and "model" not in d["config"] and d["dtype"] == "f32" and d["vs_baseline"] is None
     assert d["value"] > 500 and abs(d["value"] - d["rays_per_frame"] / d["ms_per_step"] / 1e3) < 1e-6 * d["value"]
-    assert d["gpu_launches"] == 4  # one render kernel per timed frame
+    assert d["gpu_launches"] in (4, 8)  # one render kernel (+ one drain kernel on the 8-wide tree) per timed frame
     e = d["e2e"]
     assert e["unit"] == d["unit"] and e["value"] > 0 and e["d2h_bytes_per_step"] == 1920 * 1080 * 4 and e["h2d_bytes_per_step"] > 0
     r = d["roofline"]
-    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    # the shipped scenes are cache resident: the bound is the measured L1 record-gather rate (HBM figure kept beside it)
+    assert r["bound"] == "l1_gather" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    assert r["frac_hbm_stream"] > 0 and d["frame_equals_1gpu"] is None and "run" in d and "ref_gpu_baseline" in d
     g = d["roofline_gather"]
     assert g["l1_resident_64KB"] > g["l2_resident_4MB"] > g["hbm_8GB"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

@@ -34,8 +34,8 @@ def same(a, b):
             np.array_equal(a["rgb"].view(np.uint32), b["rgb"].view(np.uint32)) and a["rays"] == b["rays"])
 
 
-VARIANTS = [dict(cull=-1, drain_k=-1), dict(cull=0, drain_k=-1), dict(cull=-1, drain_k=8), dict(cull=0, drain_k=0),
-            dict(cull=0, drain_k=32), dict(cull=0, drain_k=3, ctas_per_sm=2)]
+VARIANTS = [dict(cull=0, drain_k=0), dict(cull=1, drain_k=0), dict(cull=0, drain_k=8), dict(cull=1, drain_k=8),
+            dict(cull=1, drain_k=32), dict(cull=1, drain_k=3, ctas_per_sm=2)]
 
 
 @pytest.mark.parametrize("scene", SCENES)
@@ -48,8 +48,7 @@ def test_culling_and_drain_do_not_change_a_byte(rt, gpu_scenes, scene, wh):
     for v in VARIANTS[1:]:
         got = render(rt, ctx, w, h, traversal=rt.RT_TRAVERSAL_WIDE8, **v)
         assert same(got, base), (scene, wh, v)
-        if v["drain_k"] >= 0:
-            assert got["launches"] == 2   # render kernel + drain kernel
+        assert got["launches"] == (2 if v["drain_k"] > 0 else 1)   # render kernel (+ drain kernel)
     # against the bit-exact build: the north-star tolerances
     ctx.render_frame(rt.default_params(width=w, height=h, aov_mask=AOV, mode=rt.RT_MODE_STRICT))
     strict = ctx.load_from_gpu(rgb=True, tri_id=True, depth=True)
@@ -64,12 +63,12 @@ def test_wide8_vs_oracle_with_jitter_and_moved_camera(rt, gpu_scenes, oracle_sce
     w, h, spp = 400, 225, 4
     ref = oracle_scenes[scene].render(w, h, pos=pos, rot=rot, fov=fov, spp=spp, seed=3)
     ctx = gpu_scenes[scene][1]
-    got = render(rt, ctx, w, h, traversal=rt.RT_TRAVERSAL_WIDE8, cam=(pos, rot, fov), spp=spp, seed=3)
+    got = render(rt, ctx, w, h, traversal=rt.RT_TRAVERSAL_WIDE8, cam=(pos, rot, fov), spp=spp, seed=3, cull=1, drain_k=8)
     m = O.compare_aovs(got, ref)
     assert m["id_match"] >= 0.9999 and m["rgb8_within1"] >= 0.999 and m["depth_within_1e-4"] >= 0.9999, m
     n_ref = ref["rays_closest"] + ref["rays_shadow"]
     assert abs(sum(got["rays"]) - n_ref) <= 1e-3 * n_ref
-    plain = render(rt, ctx, w, h, traversal=rt.RT_TRAVERSAL_WIDE8, cam=(pos, rot, fov), spp=spp, seed=3, cull=-1, drain_k=-1)
+    plain = render(rt, ctx, w, h, traversal=rt.RT_TRAVERSAL_WIDE8, cam=(pos, rot, fov), spp=spp, seed=3)
     assert same(got, plain)
 
 
@@ -79,13 +78,13 @@ def test_camera_inside_and_behind_the_scene(rt, gpu_scenes):
     w, h = 320, 180
     for cam in [((0.0, 0.0, 1.0), (0.0, 0.0, 0.0), O.DEFAULT_FOV), ((0.0, -9.0, 3.0), (0.0, 0.0, 3.1), O.DEFAULT_FOV),
                 ((0.0, -40.0, 3.0), (0.3, 0.0, 0.0), 0.4), ((30.0, -9.0, 3.0), (-0.26, 0.0, 1.2), O.DEFAULT_FOV)]:
-        a = render(rt, ctx, w, h, traversal=rt.RT_TRAVERSAL_WIDE8, cam=cam, cull=-1, drain_k=-1)
-        b = render(rt, ctx, w, h, traversal=rt.RT_TRAVERSAL_WIDE8, cam=cam)
+        a = render(rt, ctx, w, h, traversal=rt.RT_TRAVERSAL_WIDE8, cam=cam)
+        b = render(rt, ctx, w, h, traversal=rt.RT_TRAVERSAL_WIDE8, cam=cam, cull=1, drain_k=8)
         assert same(a, b), cam
 
 
 @pytest.mark.parametrize("scene", ["car_only", "soup2k"])
-def test_device_built_tree_equals_host_built_tree(rt, gpu_scenes, scene):
+def test_device_built_tree_equals_host_built_tree(rt, gpu_scenes, scene, monkeypatch):
     """rt_create_gpu builds the 8-wide tree on the device with the same level-synchronous passes: same bytes."""
     sc, ctx = gpu_scenes[scene]
     host = sc.flatten_host()["nodes8"]
@@ -93,6 +92,11 @@ def test_device_built_tree_equals_host_built_tree(rt, gpu_scenes, scene):
     sc2 = rt.Scene.load_rtsc(GOLD / "scenes" / f"{scene}.rtsc")
     ctx2 = rt.Context.build_on_gpu(sc2, [0])
     assert np.array_equal(ctx2.device_array(7), host)
+    monkeypatch.setenv("RT_W8_DEVICE_BUILD", "0")       # the host-side twin of the same passes (wide8.cpp) on the device-built tree
+    sc3 = rt.Scene.load_rtsc(GOLD / "scenes" / f"{scene}.rtsc")
+    ctx3 = rt.Context.build_on_gpu(sc3, [0])
+    assert np.array_equal(ctx3.device_array(7), host)
+    ctx3.close(); sc3.close()
     a = render(rt, ctx, 480, 270, traversal=rt.RT_TRAVERSAL_WIDE8)
     b = render(rt, ctx2, 480, 270, traversal=rt.RT_TRAVERSAL_WIDE8)
     assert same(a, b)
@@ -108,7 +112,7 @@ def test_degenerate_scenes_on_the_wide_tree(rt, orc):
         sc = rt.Scene.from_arrays(tri, np.zeros(n, np.uint32), np.array([[0.2, 0.2, 0.2, 0.7, 0.6, 0.5, 0.3, 0.3, 0.3]], np.float32),
                                   np.array([[0, -8, 3, 50, 50, 50]], np.float32)).build_bvh(6)
         ctx = rt.Context(sc, [0])
-        a = render(rt, ctx, 200, 120, traversal=rt.RT_TRAVERSAL_WIDE8)
+        a = render(rt, ctx, 200, 120, traversal=rt.RT_TRAVERSAL_WIDE8, cull=1, drain_k=8)
         ctx.render_frame(rt.default_params(width=200, height=120, aov_mask=AOV, mode=rt.RT_MODE_STRICT))
         s = ctx.load_from_gpu(rgb=True, tri_id=True, depth=True)
         m = O.compare_aovs(a, s)
@@ -119,8 +123,8 @@ def test_degenerate_scenes_on_the_wide_tree(rt, orc):
     sc = rt.Scene.from_arrays(heap, np.zeros(40, np.uint32), np.array([[0.2, 0.2, 0.2, 0.7, 0.6, 0.5, 0, 0, 0]], np.float32),
                               np.array([[0, -8, 3, 50, 50, 50]], np.float32)).build_bvh(6)
     ctx = rt.Context(sc, [0])
-    a = render(rt, ctx, 200, 120, traversal=rt.RT_TRAVERSAL_WIDE8)
-    b = render(rt, ctx, 200, 120, traversal=rt.RT_TRAVERSAL_WIDE8, cull=-1, drain_k=-1)
+    a = render(rt, ctx, 200, 120, traversal=rt.RT_TRAVERSAL_WIDE8, cull=1, drain_k=8)
+    b = render(rt, ctx, 200, 120, traversal=rt.RT_TRAVERSAL_WIDE8)
     ctx.render_frame(rt.default_params(width=200, height=120, aov_mask=AOV, mode=rt.RT_MODE_STRICT))
     s = ctx.load_from_gpu(rgb=True, tri_id=True, depth=True)
     assert same(a, b)
