@@ -283,6 +283,10 @@ int rt_debug_device_array(rt_ctx* ctx, int which, void* out, size_t cap_bytes, s
 /* Roofline microbenchmark: GB/s of random 64-byte-record gathers (the shape of a node fetch, one record per
  * lane) from a working set of ws_bytes on `device` — L1-, L2- or HBM-resident depending on the size. */
 int rt_debug_gather_bandwidth(int device, size_t ws_bytes, float* gbs_out);
+/* Diagnostics: host -> device copy rate (GB/s) of `bytes` of pageable memory: mode 0 plain cudaMemcpy (the reference's way,
+ * gpu/src/gpu.cu:143-175), 1 the library's staged copy through its pinned ring (csrc/staged_copy.h), 2 cudaMemcpy from
+ * page-locked memory (the ceiling on this box). */
+int rt_debug_copy_bandwidth(int device, size_t bytes, int mode, float* gbs_out);
 /* Raw device pointer of the BGRA frame (device 0 of the context). */
 int rt_frame_device_ptr(rt_ctx* ctx, void** dev_ptr, size_t* bytes);
 

@@ -45,7 +45,7 @@ EXPORTS = [
     "rt_part_tile_count", "rt_packed_tiles", "rt_unpack_tiles", "rt_frame_ipc_export", "rt_frame_ipc_import",
     "rt_frame_device_ptr", "rt_write_bmp", "rt_abi_version", "rt_device_count", "rt_debug_warp_trace",
     "rt_render_async", "rt_download_async", "rt_frame_wait", "rt_host_alloc", "rt_host_free",
-    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order", "rt_scene_build_bvh_gpu", "rt_debug_gather_bandwidth", "rt_create_gpu", "rt_debug_flatten_host", "rt_debug_device_array",
+    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order", "rt_scene_build_bvh_gpu", "rt_debug_gather_bandwidth", "rt_create_gpu", "rt_debug_flatten_host", "rt_debug_device_array", "rt_debug_copy_bandwidth",
 ]
 
 
@@ -134,6 +134,8 @@ def lib() -> C.CDLL:
     L.rt_create.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(i32), i32, C.POINTER(vp)]
     L.rt_debug_flatten_host.argtypes = [C.POINTER(rt_scene_desc), i32, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(i32)]
     L.rt_create_gpu.argtypes = [vp, i32, C.POINTER(i32), i32, i32, C.POINTER(vp), C.POINTER(rt_bvh_gpu_stats)]
+    if hasattr(L, "rt_debug_copy_bandwidth"):
+        L.rt_debug_copy_bandwidth.argtypes = [i32, C.c_size_t, i32, C.POINTER(C.c_float)]
     if hasattr(L, "rt_debug_device_array"):  # (absent from older builds loaded through RT_B200_LIB for A/B runs)
         L.rt_debug_device_array.argtypes = [vp, i32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.rt_render.argtypes = [vp, C.POINTER(rt_render_params), C.POINTER(rt_timing)]
@@ -432,6 +434,13 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def copy_bandwidth(nbytes: int, mode: int, device: int = 0) -> float:
+    """GB/s of a host->device copy of pageable memory: 0 plain cudaMemcpy, 1 staged through the pinned ring, 2 from pinned memory."""
+    g = C.c_float()
+    _check(lib().rt_debug_copy_bandwidth(device, nbytes, mode, C.byref(g)))
+    return g.value
 
 
 def write_bmp(path, bgra: np.ndarray):

@@ -12,7 +12,9 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -206,24 +208,30 @@ __global__ void w8_encode_kernel(int n, const rt_bvh_node* __restrict__ bvh, con
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = tid >> 3, slot = tid & 7;
     if (i >= n) return;
-    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
-    int cnt = 0;
-    for (int s = 0; s < 8; s++) {
-        const int b = plan_node[8 * (size_t)i + s];
-        if (b < 0) continue;
-        const rt_bvh_node& nd = bvh[b];
-        for (int a = 0; a < 3; a++) {
-            if (!cnt || nd.min[a] < lo[a]) lo[a] = nd.min[a];
-            if (!cnt || nd.max[a] > hi[a]) hi[a] = nd.max[a];
-        }
-        cnt++;
+    // every slot contributes its child's box; the union, the child count and the grid are formed once per node (lane 0 of
+    // the eight) and handed to the other seven by shuffles (blockDim is a multiple of 32, a node never straddles a warp,
+    // and whole 8-lane groups leave together above)
+    const int mine = plan_node[8 * (size_t)i + slot];
+    const unsigned gm = 0xffu << (threadIdx.x & 24u);
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; a++) {
+        lo[a] = mine >= 0 ? bvh[mine].min[a] : INFINITY;
+        hi[a] = mine >= 0 ? bvh[mine].max[a] : -INFINITY;
     }
-    int e[3];
-    float p[3];
-    for (int a = 0; a < 3; a++) rt::w8_node_axis(lo[a], hi[a], &e[a], &p[a]);
+    for (int k = 1; k < 8; k <<= 1)
+        for (int a = 0; a < 3; a++) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(gm, lo[a], k));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(gm, hi[a], k));
+        }
+    const int cnt = __popc(__ballot_sync(gm, mine >= 0) & gm);
+    int e[3] = {0, 0, 0};
+    float p[3] = {0, 0, 0};
+    if (slot == 0)
+        for (int a = 0; a < 3; a++) rt::w8_node_axis(lo[a], hi[a], &e[a], &p[a]);
+    const int src = (int)(threadIdx.x & 24u);
+    for (int a = 0; a < 3; a++) { e[a] = __shfl_sync(gm, e[a], src); p[a] = __shfl_sync(gm, p[a], src); }
     unsigned* w = words + (size_t)(base + (unsigned)i) * rt::kWide8Words;
     unsigned char* q = reinterpret_cast<unsigned char*>(w + 4);
-    const int mine = plan_node[8 * (size_t)i + slot];
     for (int a = 0; a < 3; a++) {
         unsigned char ql = 255, qh = 0; // empty slot: inverted, never hit
         if (mine >= 0) rt::w8_quantize(bvh[mine].min[a], bvh[mine].max[a], p[a], e[a], &ql, &qh);
@@ -239,8 +247,10 @@ __global__ void w8_encode_kernel(int n, const rt_bvh_node* __restrict__ bvh, con
 
 struct Buf {
     void* p = nullptr;
-    ~Buf() { cudaFree(p); }
+    bool pooled = false; // stream-ordered allocation (cudaMallocAsync on the default stream): no device-wide sync per free
+    ~Buf() { if (pooled) cudaFreeAsync(p, 0); else cudaFree(p); }
     cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    cudaError_t alloc_pooled(size_t bytes) { pooled = true; return cudaMallocAsync(&p, bytes ? bytes : 16, 0); }
     template <class T> T* as() const { return static_cast<T*>(p); }
     template <class T> T* take() { T* r = static_cast<T*>(p); p = nullptr; return r; }
 };
@@ -250,6 +260,15 @@ struct Buf {
 int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_mats, DeviceFlat& out, std::string& err)
 {
 #define CKF(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { err = std::string("flatten_gpu: ") + #call + " failed: " + cudaGetErrorString(e__); return RT_ERR_CUDA; } } while (0)
+    const bool timing = std::getenv("RT_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto stage = [&](const char* what) {
+        if (!timing) return;
+        cudaDeviceSynchronize();
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[flatten_gpu] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     const int n = (int)t.n_tris, nn = (int)t.n_nodes;
     if (n < 1 || nn < 3) { err = "flatten_gpu: the tree has no inner node"; return RT_ERR_INVALID; }
     const size_t n_inner = (size_t)(nn - 1) / 2; // every split allocated two nodes
@@ -266,6 +285,7 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
         CKF(mat.alloc((size_t)n * 4));
         CKF(rt::staged_h2d(mat.p, host_tri_mat, (size_t)n * 4, 0));
     }
+    stage("alloc + tri_mat upload");
     const int B = 256;
     tris_kernel<<<(n + B - 1) / B, B>>>(n, t.tri, t.tri_idx, tris.as<float4>());
     shade_kernel<<<(n + B - 1) / B, B>>>(n, t.tri, host_tri_mat ? mat.as<unsigned>() : nullptr, n_mats ? n_mats : 1u, shade.as<float4>(), flags.as<FlatFlags>());
@@ -282,6 +302,7 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
         nodes_kernel<<<(nn + B - 1) / B, B>>>(nn, n, t.nodes, t.depth, nodes.as<float4>(), is_even.as<int>(), leaf_cnt.as<int>(), flags.as<FlatFlags>());
         CKF(cudaGetLastError());
     }
+    stage("tris / shade / nodes");
     // 4-wide node indices: exclusive scan of the even-depth flags in pre-order
     size_t tmp_bytes = 0;
     CKF(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, is_even.as<int>(), idx4.as<int>(), (int)n_inner));
@@ -301,6 +322,7 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
     CKF(cudaGetLastError());
     int need_root = 0;
     CKF(cudaMemcpy(&need_root, need4.p, 4, cudaMemcpyDeviceToHost));
+    stage("4-wide nodes");
     // ---- compressed 8-wide tree: first the node lists of all levels (sizes), then the records ----
     Buf nodes8;
     size_t n8 = 0;
@@ -320,9 +342,16 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
     } else {
         std::vector<Buf> lists, plan_nodes, plan_refs;   // per level: node list, (node, slot) plan
         std::vector<int> sizes;
+        {   // keep freed blocks in the pool between levels instead of returning them to the driver
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, t.device) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+        }
         lists.reserve(72); plan_nodes.reserve(72); plan_refs.reserve(72); // (Buf is not movable: no reallocation; <= 66 levels, checked below)
         lists.emplace_back();
-        CKF(lists[0].alloc(4));
+        CKF(lists[0].alloc_pooled(4));
         CKF(cudaMemset(lists[0].p, 0, 4)); // level 0 = {reference node 0}
         sizes.push_back(1);
         Buf tmp;
@@ -335,31 +364,31 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
             if (lv > 64) { err = "flatten_gpu: 8-wide tree deeper than 64 levels"; return RT_ERR_INVALID; }
             const int m = sizes[lv];
             Buf c2, off;
-            CKF(c2.alloc(((size_t)m + 1) * 4));
+            CKF(c2.alloc_pooled(((size_t)m + 1) * 4));
             CKF(cudaMemset(c2.p, 0, ((size_t)m + 1) * 4));
             w8_count_kernel<<<(m + 127) / 128, 128>>>(m, leaf_max, lists[lv].as<unsigned>(), t.nodes, c2.as<int>());
             CKL("w8_count_kernel");
-            CKF(off.alloc(((size_t)m + 1) * 4));
+            CKF(off.alloc_pooled(((size_t)m + 1) * 4));
             size_t need = 0;
             CKF(cub::DeviceScan::ExclusiveSum(nullptr, need, c2.as<int>(), off.as<int>(), m + 1));
-            if (need > tmp_cap) { cudaFree(tmp.p); tmp.p = nullptr; CKF(tmp.alloc(need)); tmp_cap = need; }
+            if (need > tmp_cap) { if (tmp.p) cudaFreeAsync(tmp.p, 0); tmp.p = nullptr; CKF(tmp.alloc_pooled(need)); tmp_cap = need; }
             CKF(cub::DeviceScan::ExclusiveSum(tmp.p, need, c2.as<int>(), off.as<int>(), m + 1));
             int total = 0;
             CKF(cudaMemcpy(&total, off.as<int>() + m, 4, cudaMemcpyDeviceToHost));
             lists.emplace_back(); plan_nodes.emplace_back(); plan_refs.emplace_back();
-            CKF(lists[lv + 1].alloc((size_t)std::max(total, 1) * 4));
-            CKF(plan_nodes[lv].alloc((size_t)m * 32));
-            CKF(plan_refs[lv].alloc((size_t)m * 32));
+            CKF(lists[lv + 1].alloc_pooled((size_t)std::max(total, 1) * 4));
+            CKF(plan_nodes[lv].alloc_pooled((size_t)m * 32));
+            CKF(plan_refs[lv].alloc_pooled((size_t)m * 32));
             w8_plan_kernel<<<(m + 127) / 128, 128>>>(m, leaf_max, lists[lv].as<unsigned>(), t.nodes, off.as<int>(), (unsigned)(done + (size_t)m),
                                                      lists[lv + 1].as<unsigned>(), plan_nodes[lv].as<int>(), plan_refs[lv].as<int>());
             CKF(cudaGetLastError());
             CKL("w8_plan_kernel");
-            CKF(cudaDeviceSynchronize()); // (c2 / off are freed at the end of the iteration)
             sizes.push_back(total);
             done += (size_t)m;
             n8 += (size_t)m;
             depth8++;
         }
+        stage("8-wide: levels (count/scan/plan)");
         CKF(nodes8.alloc(n8 * 96));
         size_t base = 0;
         for (int lv = 0; lv < depth8; lv++) {

@@ -8,7 +8,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -461,7 +463,9 @@ int rt_create_gpu(rt_scene* s, int heuristic, const int* devices, int ndev, int 
     rt::flatten_small(d, small);
     rt::DeviceFlat df;
     std::string err;
+    const auto t_f0 = std::chrono::steady_clock::now();
     rc = rt::flatten_gpu(tree, s->tri_mat.empty() ? nullptr : s->tri_mat.data(), s->n_mats(), df, err);
+    if (std::getenv("RT_TIMING")) std::fprintf(stderr, "[rt_create_gpu] device-side flatten %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_f0).count());
     tree.release();
     if (rc) {
         cudaFree(df.nodes); cudaFree(df.nodes4); cudaFree(df.nodes8); cudaFree(df.tris); cudaFree(df.shade); cudaFree(df.leaf_cnt);
@@ -987,6 +991,43 @@ int rt_debug_gather_bandwidth(int device, size_t ws_bytes, float* gbs_out)
     if (e1) cudaEventDestroy(e1);
     cudaFree(data); cudaFree(sink);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, RT_ERR_CUDA, std::string("rt_debug_gather_bandwidth: ") + cudaGetErrorString(e)); }
+    *gbs_out = best;
+    return RT_OK;
+}
+
+// Host -> device copy rate of `bytes` from pageable memory: mode 0 = plain cudaMemcpy (what the reference does,
+// gpu/src/gpu.cu:143-175), 1 = the library's staged copy through the pinned ring (staged_copy.h), 2 = cudaMemcpy from
+// page-locked memory (the ceiling).  GB/s of the best of three repetitions.
+int rt_debug_copy_bandwidth(int device, size_t bytes, int mode, float* gbs_out)
+{
+    if (!gbs_out || bytes < 4096 || mode < 0 || mode > 2) return fail(nullptr, RT_ERR_INVALID, "rt_debug_copy_bandwidth: bad argument");
+    if (rt_device_count() <= device || device < 0) return fail(nullptr, RT_ERR_NO_DEVICE, "rt_debug_copy_bandwidth: no such device");
+    void* dst = nullptr;
+    void* pinned = nullptr;
+    std::vector<char> src;
+    float best = 0.f;
+    auto run = [&]() -> cudaError_t {
+        cudaError_t e;
+        if ((e = cudaSetDevice(device)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&dst, bytes)) != cudaSuccess) return e;
+        if (mode == 2) { if ((e = cudaHostAlloc(&pinned, bytes, cudaHostAllocDefault)) != cudaSuccess) return e; std::memset(pinned, 1, bytes); }
+        else src.assign(bytes, 1);
+        for (int rep = 0; rep < 3; rep++) {
+            const auto t0 = std::chrono::steady_clock::now();
+            if (mode == 0) e = cudaMemcpy(dst, src.data(), bytes, cudaMemcpyHostToDevice);
+            else if (mode == 1) e = rt::staged_h2d(dst, src.data(), bytes, 0);
+            else e = cudaMemcpy(dst, pinned, bytes, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) return e;
+            if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
+            const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            best = std::max(best, (float)(bytes / s / 1e9));
+        }
+        return cudaSuccess;
+    };
+    const cudaError_t e = run();
+    cudaFree(dst);
+    if (pinned) cudaFreeHost(pinned);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, RT_ERR_CUDA, std::string("rt_debug_copy_bandwidth: ") + cudaGetErrorString(e)); }
     *gbs_out = best;
     return RT_OK;
 }

@@ -4,7 +4,8 @@ Triangles -> render-ready context entirely on the device (rt_create_gpu: staged 
 flatten incl. the compressed 8-wide tree), then every fast traversal variant against the strict build, kernel ms (median),
 the byte counts of the scene arrays, and one strict RT_AOV_WORK pass for the algorithmic bytes.  JSON lines on stdout.
 usage: python scripts/config5.py [nx ny] [frames]"""
-import json, statistics, sys, time
+import json, os, statistics, sys, time
+os.environ.setdefault("RT_TIMING", "1")
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
@@ -18,6 +19,10 @@ def main():
     frames = int(sys.argv[3]) if len(sys.argv) > 3 else 8
     W, H = 3840, 2160
     base = rt.Scene.load_rtsc(ROOT / "tests" / "golden" / "scenes" / "car_only.rtsc")
+    warm = rt.Context.build_on_gpu(rt.Scene.load_rtsc(ROOT / "tests" / "golden" / "scenes" / "car_only.rtsc"), [0])  # CUDA context, module load
+    warm.close()
+    print(json.dumps({"h2d_gbs_1GB": {"pageable_cudaMemcpy": round(rt.copy_bandwidth(1 << 30, 0), 2), "staged_pinned_ring": round(rt.copy_bandwidth(1 << 30, 1), 2),
+                                       "pinned_cudaMemcpy": round(rt.copy_bandwidth(1 << 30, 2), 2)}}), flush=True)
     t0 = time.perf_counter()
     big = base.instance_grid(nx, ny, 1, (11.5, 6.5, 3.0))
     t1 = time.perf_counter()
