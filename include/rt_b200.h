@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 2
+#define RT_B200_ABI_VERSION 3
 #define RT_MAX_DEVICES 16
 
 typedef enum rt_status {
@@ -193,6 +193,11 @@ typedef struct rt_render_params {
     int32_t   drain_k;          /* once the chunk queue is empty, a warp left with <= drain_k live pixels hands them to the
                                    cooperative drain kernel (eight lanes per ray) */
     int32_t   cull;             /* test every 8x4-pixel chunk's ray pyramid against the top of the tree before tracing it */
+    /* fast build: 0 = heaviest pixels first — every frame records its per-pixel traversal cost, and the next frame of the same
+     * shape (size, spp, partition) on this context starts with the pixels that were most expensive (frame sequences are
+     * coherent; a wrong guess only costs time, the bytes of a pixel do not depend on when it is rendered); < 0 = chunk order only */
+    int32_t   schedule;
+    int32_t   reserved;
 } rt_render_params;
 
 typedef struct rt_timing {

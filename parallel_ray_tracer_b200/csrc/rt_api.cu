@@ -56,6 +56,16 @@ struct Dev {
     uchar4* packed = nullptr; // packed tiles (gather paths)
     size_t packed_px = 0;
     bool peer_to_0 = false;
+    // heaviest-pixels-first scheduling (fast build): per-pixel traversal cost of the last two frames (ping-pong), the list
+    // selected from the newer one, its header {count, threshold bin, T1, T2, T3, -, -, -, hist[256]}, and what it belongs to
+    unsigned short* cost[2] = {nullptr, nullptr};
+    size_t cost_px = 0;
+    unsigned* heavy_list = nullptr;
+    size_t heavy_cap = 0;
+    unsigned* heavy_hdr = nullptr;
+    int cost_cur = 0;
+    bool cost_valid = false;
+    int cost_key[5] = {0, 0, 0, 0, 0}; // width, height, spp, part_index, part_count
     RtPathRec* drain_queue[RT_FRAME_SLOTS] = {}; // tail hand-off queue per frame slot (render_kernel.cuh: drain_kernel)
     size_t drain_cap[RT_FRAME_SLOTS] = {};
     unsigned long long* warp_trace = nullptr; // diagnostics (rt_debug_warp_trace)
@@ -174,6 +184,63 @@ __global__ void unpack_tiles_kernel(uchar4* __restrict__ frame, const uchar4* __
     frame[(size_t)y * width + x] = gathered[(size_t)owner * stride_px + (size_t)li * RT_TILE_PIXELS + p];
 }
 
+// ------------------------------------------------------------------ heaviest pixels first
+// The frame time of a small frame is the dependent chain of its heaviest pixels (8 rays x hundreds of traversal steps) counted
+// from the moment they START (profiles/r02_notes.md §6): a heavy pixel fetched when the chunk queue is nearly empty ends the frame
+// half a millisecond later, alone on its SM.  Frame sequences are coherent, so the kernel records every pixel's traversal steps
+// (RtFrameArgs::cost_out) and the three small kernels below turn that map into the list of pixels the NEXT frame of the same
+// shape starts with, heaviest first.  Scheduling only: a pixel's bytes do not depend on when or where it is rendered.
+__global__ void cost_hist_kernel(const unsigned short* __restrict__ cost, size_t n, unsigned* __restrict__ hdr)
+{
+    __shared__ unsigned h[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned b = (unsigned)cost[i] >> RT_COST_SHIFT;
+        if (b) atomicAdd(&h[b < 255u ? b : 255u], 1u); // (bin 0 = background and never-rendered pixels: not counted)
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) if (h[i]) atomicAdd(&hdr[8 + i], h[i]);
+}
+// one thread: thresholds T1 >= T2 >= T3 = 1/2, 1/4, 1/8 of the highest occupied bin, raised until the list fits `cap`
+__global__ void cost_threshold_kernel(unsigned* __restrict__ hdr, unsigned cap)
+{
+    const unsigned* hist = hdr + 8;
+    int bmax = 0;
+    for (int b = 255; b >= 1; b--) if (hist[b]) { bmax = b; break; }
+    unsigned t1 = 256, t2 = 256, t3 = 256;
+    if (bmax >= 8) { // (frames whose heaviest pixel takes < 64 steps have no tail worth scheduling)
+        t3 = (unsigned)bmax / 8u; if (t3 < 2u) t3 = 2u;
+        unsigned cum = 0;
+        unsigned lowest = 256;
+        for (int b = 255; b >= (int)t3; b--) { if (cum + hist[b] > cap) break; cum += hist[b]; lowest = (unsigned)b; }
+        t3 = lowest;
+        t2 = (unsigned)bmax / 4u > t3 ? (unsigned)bmax / 4u : t3;
+        t1 = (unsigned)bmax / 2u > t2 ? (unsigned)bmax / 2u : t2;
+    }
+    hdr[0] = 0; hdr[1] = t3; hdr[2] = t1; hdr[3] = t2; hdr[4] = t3;
+}
+// append the pixels whose bin lies in [hdr[2 + pass], upper) to the list; pass 0: upper = 256, else upper = hdr[1 + pass]
+__global__ void cost_compact_kernel(const unsigned short* __restrict__ cost, int width, int height, int pass, unsigned* __restrict__ hdr,
+                                    unsigned* __restrict__ list, unsigned cap)
+{
+    const unsigned lo = hdr[2 + pass], hi = pass == 0 ? 256u : hdr[1 + pass];
+    if (lo >= hi) return;
+    const size_t n = (size_t)width * height;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n + 31; i += (size_t)gridDim.x * blockDim.x) {
+        bool sel = false;
+        if (i < n) { unsigned b = (unsigned)cost[i] >> RT_COST_SHIFT; b = b < 255u ? b : 255u; sel = b >= lo && b < hi; }
+        const unsigned m = __ballot_sync(0xffffffffu, sel);
+        if (!m) continue;
+        unsigned base = 0;
+        const unsigned lane = threadIdx.x & 31u;
+        if (lane == 0) base = atomicAdd(&hdr[0], (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned pos = base + (unsigned)__popc(m & ((1u << lane) - 1u));
+        if (sel && pos < cap) list[pos] = (unsigned)(i % (size_t)width) | ((unsigned)(i / (size_t)width) << 16);
+    }
+}
+
 // Microbenchmark for the roofline: every lane gathers its own random 64-byte record (two 256-bit loads, the
 // shape of an inner-node fetch) from a working set of `n_rec` records; four independent gathers in flight per lane.
 __global__ void gather64_kernel(const float4* __restrict__ data, unsigned n_rec_mask, int iters, unsigned seed, float4* sink)
@@ -273,6 +340,7 @@ void free_dev(Dev& D)
     cudaFree(D.leaf_cnt); cudaFree(D.ctrl); cudaFree(D.tile_list); cudaFree(D.warp_trace);
     cudaFree(D.bgra); cudaFree(D.packed);
     for (int s = 0; s < RT_FRAME_SLOTS; s++) cudaFree(D.drain_queue[s]);
+    cudaFree(D.cost[0]); cudaFree(D.cost[1]); cudaFree(D.heavy_list); cudaFree(D.heavy_hdr);
     if (D.ctrl_host) cudaFreeHost(D.ctrl_host);
     for (int s = 0; s < RT_FRAME_SLOTS; s++) {
         if (D.ev0[s]) cudaEventDestroy(D.ev0[s]);
@@ -659,6 +727,29 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         const int warps_needed = (D.n_tiles * (RT_TILE_PIXELS / 32) + (cf.block_threads / 32) - 1) / (cf.block_threads / 32);
         if (warps_needed < cf.grid) cf.grid = std::max(warps_needed, 1);
 
+        // heaviest pixels first: this frame records costs into the other buffer and, when the previous frame had this shape,
+        // starts with the list selected from that frame's costs
+        f.cost_out = nullptr; f.cost_prev = nullptr; f.heavy_list = nullptr; f.heavy_hdr = nullptr;
+        f.heavy_counter = reinterpret_cast<unsigned*>(ctrl + 4) + 1;
+        const bool track_cost = p->mode == RT_MODE_FAST && cfg.wide != 0 && !cf.work_counters && p->schedule >= 0 && p->bounces > 0;
+        const int key[5] = {w, h, p->spp, p->part_index, part_count};
+        if (track_cost) {
+            const size_t cap = npx / 8 + 64;
+            if (D.cost_px < npx) { // (re)allocate: the maps start empty
+                CK(c, cudaStreamSynchronize(D.stream));
+                cudaFree(D.cost[0]); cudaFree(D.cost[1]); cudaFree(D.heavy_list);
+                D.cost[0] = D.cost[1] = nullptr; D.heavy_list = nullptr; D.cost_px = 0; D.cost_valid = false;
+                CK(c, cudaMalloc((void**)&D.cost[0], npx * 2)); CK(c, cudaMalloc((void**)&D.cost[1], npx * 2));
+                CK(c, cudaMalloc((void**)&D.heavy_list, cap * 4));
+                if (!D.heavy_hdr) CK(c, cudaMalloc((void**)&D.heavy_hdr, (8 + 256) * 4));
+                D.cost_px = npx; D.heavy_cap = cap;
+            }
+            if (std::memcmp(key, D.cost_key, sizeof key) != 0) D.cost_valid = false;
+            const int nxt = 1 - D.cost_cur;
+            CK(c, cudaMemsetAsync(D.cost[nxt], 0, npx * 2, D.stream)); // pixels of other parts stay 0 = never heavy
+            f.cost_out = D.cost[nxt];
+            if (D.cost_valid) { f.cost_prev = D.cost[D.cost_cur]; f.heavy_list = D.heavy_list; f.heavy_hdr = D.heavy_hdr; }
+        }
         f.drain_k = 0; f.drain_queue = nullptr; f.drain_cap = 0;
         f.drain_count = reinterpret_cast<unsigned*>(ctrl + 5); f.drain_next = reinterpret_cast<unsigned*>(ctrl + 6);
         if (drain_k > 0) {
@@ -684,6 +775,18 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         if (f.drain_k > 0) { // the paths the render kernel's warps handed off at the end of the chunk queue
             CK(c, rt_launch_drain(sc, f, cf.work_counters, D.sm_count, D.stream));
             launches++;
+        }
+        if (track_cost) { // select the pixels the next frame of this shape starts with (inside this frame's timed window)
+            const unsigned cap = (unsigned)(npx / 8);
+            CK(c, cudaMemsetAsync(D.heavy_hdr, 0, (8 + 256) * 4, D.stream));
+            cost_hist_kernel<<<D.sm_count * 2, 256, 0, D.stream>>>(f.cost_out, npx, D.heavy_hdr);
+            cost_threshold_kernel<<<1, 1, 0, D.stream>>>(D.heavy_hdr, cap);
+            for (int pass = 0; pass < 3; pass++)
+                cost_compact_kernel<<<D.sm_count * 2, 256, 0, D.stream>>>(f.cost_out, w, h, pass, D.heavy_hdr, D.heavy_list, cap);
+            CK(c, cudaGetLastError());
+            launches += 5;
+            D.cost_cur = 1 - D.cost_cur; D.cost_valid = true;
+            std::memcpy(D.cost_key, key, sizeof key);
         }
         CK(c, cudaEventRecord(D.ev1[slot], D.stream));
         // statistics -> pinned host memory on the second stream (this slot's control block is not touched again before

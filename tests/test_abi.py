@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(rt):
     lib = rt.lib()
     for name in rt.EXPORTS:
         assert getattr(lib, name) is not None
-    assert lib.rt_abi_version() == 2
+    assert lib.rt_abi_version() == 3
 
 
 def test_no_torch_or_cxx_types_cross_the_boundary():

@@ -1,0 +1,77 @@
+"""Heaviest-pixels-first scheduling (rt_render_params.schedule = 0, the default of the fast build on the wide trees): every
+frame records its per-pixel traversal cost and the next frame of the same shape starts with the most expensive pixels.
+It is scheduling only — the bytes of a pixel must not depend on when or by which warp it is rendered, whether the cost map
+is fresh, stale (the camera moved) or absent (first frame, new resolution, new partition)."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+AOV = 1 | 2 | 4
+
+
+@pytest.fixture(autouse=True)
+def _need_gpu(rt):
+    if rt.device_count() < 1:
+        pytest.skip("no CUDA device")
+
+
+def render(rt, ctx, w, h, **kw):
+    tm = ctx.render_frame(rt.default_params(width=w, height=h, aov_mask=AOV, **kw))
+    out = {k: v.copy() for k, v in ctx.load_from_gpu(rgb=True, tri_id=True, depth=True).items()}
+    out["rays"] = (tm.rays_closest, tm.rays_shadow)
+    out["launches"] = tm.launches
+    return out
+
+
+def same(a, b):
+    return (np.array_equal(a["bgra"], b["bgra"]) and np.array_equal(a["id"], b["id"]) and
+            np.array_equal(a["depth"].view(np.uint32), b["depth"].view(np.uint32)) and
+            np.array_equal(a["rgb"].view(np.uint32), b["rgb"].view(np.uint32)) and a["rays"] == b["rays"])
+
+
+@pytest.mark.parametrize("scene", ["car_only", "car_boxed", "soup2k"])
+@pytest.mark.parametrize("traversal", [3, 4])
+def test_heavy_first_frames_equal_chunk_order_frames(rt, gpu_scenes, scene, traversal):
+    sc, _ = gpu_scenes[scene]
+    ctx = rt.Context(sc, [0])          # a context of its own: the cost history starts empty
+    w, h = 960, 540
+    plain = render(rt, ctx, w, h, traversal=traversal, schedule=-1)
+    assert plain["launches"] == 1
+    for k in range(3):                 # frame 0 has no history, frames 1-2 start with the heavy list
+        got = render(rt, ctx, w, h, traversal=traversal)
+        assert got["launches"] == 6    # render kernel + histogram, threshold, 3 compaction passes
+        assert same(got, plain), (scene, traversal, k)
+    # stale map: the camera moved between the frame that produced the map and the frame that uses it
+    cam = (O.DEFAULT_CAM_POS, (O.DEFAULT_CAM_ROT[0], 0.0, 0.35), O.DEFAULT_FOV)
+    moved = render(rt, ctx, w, h, traversal=traversal, cam=cam)
+    assert same(moved, render(rt, ctx, w, h, traversal=traversal, cam=cam, schedule=-1))
+    # new shape, new partition, supersampling: the history is dropped / rebuilt
+    for kw in (dict(width=500, height=281), dict(width=960, height=540, part_index=1, part_count=3), dict(width=320, height=180, spp=3)):
+        wh = (kw.pop("width"), kw.pop("height"))
+        ref = render(rt, ctx, *wh, traversal=traversal, schedule=-1, **kw)
+        for _ in range(2):
+            assert same(render(rt, ctx, *wh, traversal=traversal, **kw), ref), kw
+    ctx.close()
+
+
+def test_pipelined_sequence_with_history(rt, gpu_scenes):
+    """Two frame slots in flight: frame k + 1 is queued while frame k's cost map is still being produced (stream order)."""
+    sc, _ = gpu_scenes["car_only"]
+    ctx = rt.Context(sc, [0])
+    w, h = 640, 360
+    ctx.render_frame(rt.default_params(width=w, height=h, schedule=-1))
+    want = ctx.load_from_gpu()["bgra"].copy()
+    bufs = [rt.PinnedBuffer(w * h * 4) for _ in range(2)]
+    for k in range(6):
+        s = k % 2
+        if k >= 2:
+            ctx.frame_wait(s)
+            assert np.array_equal(bufs[s].array.reshape(h, w, 4), want)
+        ctx.render_frame_async(rt.default_params(width=w, height=h, frame_slot=s))
+        ctx.download_async(s, bufs[s].ptr)
+    for s in (0, 1):
+        ctx.frame_wait(s)
+        assert np.array_equal(bufs[s].array.reshape(h, w, 4), want)
+    ctx.close()

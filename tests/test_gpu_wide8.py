@@ -43,12 +43,13 @@ VARIANTS = [dict(cull=0, drain_k=0), dict(cull=1, drain_k=0), dict(cull=0, drain
 def test_culling_and_drain_do_not_change_a_byte(rt, gpu_scenes, scene, wh):
     w, h = wh
     ctx = gpu_scenes[scene][1]
-    base = render(rt, ctx, w, h, traversal=rt.RT_TRAVERSAL_WIDE8, **VARIANTS[0])
+    base = render(rt, ctx, w, h, traversal=rt.RT_TRAVERSAL_WIDE8, schedule=-1, **VARIANTS[0])
     assert base["launches"] == 1
     for v in VARIANTS[1:]:
-        got = render(rt, ctx, w, h, traversal=rt.RT_TRAVERSAL_WIDE8, **v)
+        got = render(rt, ctx, w, h, traversal=rt.RT_TRAVERSAL_WIDE8, schedule=-1, **v)
         assert same(got, base), (scene, wh, v)
         assert got["launches"] == (2 if v["drain_k"] > 0 else 1)   # render kernel (+ drain kernel)
+        assert same(render(rt, ctx, w, h, traversal=rt.RT_TRAVERSAL_WIDE8, **v), base), (scene, wh, v, "heavy first")
     # against the bit-exact build: the north-star tolerances
     ctx.render_frame(rt.default_params(width=w, height=h, aov_mask=AOV, mode=rt.RT_MODE_STRICT))
     strict = ctx.load_from_gpu(rgb=True, tri_id=True, depth=True)
