@@ -71,7 +71,6 @@ struct RtPathRec {
     float P[3], n[3], in[3], pend[3];
     int   mat, li, culled, pad;
 };
-#define RT_COST_SHIFT 3 /* cost bins of 8 traversal steps */
 #define RT_DRAIN_STACK 96 /* per-path stack of the drain kernel: (child ref, entry distance) pairs, up to 7 per level */
 
 struct RtFrameArgs {
@@ -88,13 +87,15 @@ struct RtFrameArgs {
     unsigned n_sms;
     int   refill_threshold;
     int   cull;                    // fast build: test every chunk's ray pyramid against the top of nodes8 first (needs sc.nodes8)
-    // fast build, heaviest pixels first (rt_api.cu: heavy-pixel selection).  cost_out receives every pixel's traversal
-    // steps; heavy_list holds the pixels (x | y << 16) whose cost in the PREVIOUS frame of this shape reached heavy_hdr[1]
-    // cost bins (heaviest first): the warps take those before the regular chunks, and skip them there (cost_prev).
+    // fast build, heaviest pixels first (rt_api.cu: cost_select_kernel).  cost_out receives every pixel's traversal steps (15
+    // bits) and heavy_hdr_out[1] their maximum; heavy_list holds the pixels (x | y << 16) the selection took from the PREVIOUS
+    // frame of this shape — flagged with bit 15 in cost_prev — which the warps render before the regular chunks and skip there.
     unsigned short* cost_out;
     const unsigned short* cost_prev;
     const unsigned* heavy_list;
-    const unsigned* heavy_hdr;     // [0] entries in heavy_list, [1] threshold bin (bin = min(cost >> RT_COST_SHIFT, 255))
+    const unsigned* heavy_hdr;     // [0] pixels the selection counted (entries = min(that, heavy_cap))
+    unsigned heavy_cap;
+    unsigned* heavy_hdr_out;       // [1] = max cost of this frame
     unsigned* heavy_counter;       // next heavy_list entry to hand out (zeroed per frame)
     // fast build, tail of the frame: once the chunk queue is empty, a warp left with <= drain_k live pixels writes their
     // paths to drain_queue and exits; drain_kernel finishes them with eight lanes per ray (0 = off)

@@ -56,8 +56,8 @@ struct Dev {
     uchar4* packed = nullptr; // packed tiles (gather paths)
     size_t packed_px = 0;
     bool peer_to_0 = false;
-    // heaviest-pixels-first scheduling (fast build): per-pixel traversal cost of the last two frames (ping-pong), the list
-    // selected from the newer one, its header {count, threshold bin, T1, T2, T3, -, -, -, hist[256]}, and what it belongs to
+    // heaviest-pixels-first scheduling (fast build): per-pixel traversal cost of the last two frames (ping-pong; bit 15 = "in the
+    // list"), the list selected from the newer one, two headers {entries, largest cost, -, -} (ping-pong), and what it belongs to
     unsigned short* cost[2] = {nullptr, nullptr};
     size_t cost_px = 0;
     unsigned* heavy_list = nullptr;
@@ -188,56 +188,34 @@ __global__ void unpack_tiles_kernel(uchar4* __restrict__ frame, const uchar4* __
 // The frame time of a small frame is the dependent chain of its heaviest pixels (8 rays x hundreds of traversal steps) counted
 // from the moment they START (profiles/r02_notes.md §6): a heavy pixel fetched when the chunk queue is nearly empty ends the frame
 // half a millisecond later, alone on its SM.  Frame sequences are coherent, so the kernel records every pixel's traversal steps
-// (RtFrameArgs::cost_out) and the three small kernels below turn that map into the list of pixels the NEXT frame of the same
-// shape starts with, heaviest first.  Scheduling only: a pixel's bytes do not depend on when or where it is rendered.
-__global__ void cost_hist_kernel(const unsigned short* __restrict__ cost, size_t n, unsigned* __restrict__ hdr)
+// (RtFrameArgs::cost_out, 15 bits) and the largest of them (heavy_hdr_out[1]); the kernel below then lists the pixels that took at
+// least a fraction of that maximum — walking the frame chunk by chunk, so that 32 consecutive entries are neighbours — and flags
+// them in the map (bit 15).  The NEXT frame of the same shape starts with that list and skips flagged pixels in the regular
+// chunks.  Scheduling only: a pixel's bytes do not depend on when or where it is rendered.
+__global__ void cost_select_kernel(unsigned short* __restrict__ cost, int width, int height, int tiles_x, unsigned n_chunks, unsigned* __restrict__ hdr,
+                                   unsigned* __restrict__ list, unsigned cap, float frac)
 {
-    __shared__ unsigned h[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) h[i] = 0;
-    __syncthreads();
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const unsigned b = (unsigned)cost[i] >> RT_COST_SHIFT;
-        if (b) atomicAdd(&h[b < 255u ? b : 255u], 1u); // (bin 0 = background and never-rendered pixels: not counted)
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) if (h[i]) atomicAdd(&hdr[8 + i], h[i]);
-}
-// one thread: thresholds T1 >= T2 >= T3 = 1/2, 1/4, 1/8 of the highest occupied bin, raised until the list fits `cap`
-__global__ void cost_threshold_kernel(unsigned* __restrict__ hdr, unsigned cap)
-{
-    const unsigned* hist = hdr + 8;
-    int bmax = 0;
-    for (int b = 255; b >= 1; b--) if (hist[b]) { bmax = b; break; }
-    unsigned t1 = 256, t2 = 256, t3 = 256;
-    if (bmax >= 8) { // (frames whose heaviest pixel takes < 64 steps have no tail worth scheduling)
-        t3 = (unsigned)bmax / 8u; if (t3 < 2u) t3 = 2u;
-        unsigned cum = 0;
-        unsigned lowest = 256;
-        for (int b = 255; b >= (int)t3; b--) { if (cum + hist[b] > cap) break; cum += hist[b]; lowest = (unsigned)b; }
-        t3 = lowest;
-        t2 = (unsigned)bmax / 4u > t3 ? (unsigned)bmax / 4u : t3;
-        t1 = (unsigned)bmax / 2u > t2 ? (unsigned)bmax / 2u : t2;
-    }
-    hdr[0] = 0; hdr[1] = t3; hdr[2] = t1; hdr[3] = t2; hdr[4] = t3;
-}
-// append the pixels whose bin lies in [hdr[2 + pass], upper) to the list; pass 0: upper = 256, else upper = hdr[1 + pass]
-__global__ void cost_compact_kernel(const unsigned short* __restrict__ cost, int width, int height, int pass, unsigned* __restrict__ hdr,
-                                    unsigned* __restrict__ list, unsigned cap)
-{
-    const unsigned lo = hdr[2 + pass], hi = pass == 0 ? 256u : hdr[1 + pass];
-    if (lo >= hi) return;
-    const size_t n = (size_t)width * height;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n + 31; i += (size_t)gridDim.x * blockDim.x) {
-        bool sel = false;
-        if (i < n) { unsigned b = (unsigned)cost[i] >> RT_COST_SHIFT; b = b < 255u ? b : 255u; sel = b >= lo && b < hi; }
+    const unsigned mx = hdr[1];
+    unsigned thr = (unsigned)((float)mx * frac);
+    if (thr < 48u) thr = 48u;           // (a frame whose heaviest pixel takes a few dozen steps has no tail worth scheduling)
+    if (mx < 96u) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned c = warp; c < n_chunks; c += n_warps) {   // one 8x4 chunk per warp iteration (render_kernel's pixel order)
+        const unsigned tile = c >> 2, b = c & 3u;
+        const int x = (int)(tile % (unsigned)tiles_x) * RT_TILE_W + (int)((b & 1u) << 3) + (int)(lane & 7u);
+        const int y = (int)(tile / (unsigned)tiles_x) * RT_TILE_H + (int)((b >> 1) << 2) + (int)(lane >> 3);
+        const bool in = x < width && y < height;
+        const size_t i = (size_t)y * width + x;
+        const unsigned v = in ? cost[i] : 0u;
+        const bool sel = in && (v & 0x7fffu) >= thr;
         const unsigned m = __ballot_sync(0xffffffffu, sel);
         if (!m) continue;
         unsigned base = 0;
-        const unsigned lane = threadIdx.x & 31u;
         if (lane == 0) base = atomicAdd(&hdr[0], (unsigned)__popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
         const unsigned pos = base + (unsigned)__popc(m & ((1u << lane) - 1u));
-        if (sel && pos < cap) list[pos] = (unsigned)(i % (size_t)width) | ((unsigned)(i / (size_t)width) << 16);
+        if (sel && pos < cap) { list[pos] = (unsigned)x | ((unsigned)y << 16); cost[i] = (unsigned short)(v | 0x8000u); }
     }
 }
 
@@ -729,26 +707,33 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
 
         // heaviest pixels first: this frame records costs into the other buffer and, when the previous frame had this shape,
         // starts with the list selected from that frame's costs
-        f.cost_out = nullptr; f.cost_prev = nullptr; f.heavy_list = nullptr; f.heavy_hdr = nullptr;
+        f.cost_out = nullptr; f.cost_prev = nullptr; f.heavy_list = nullptr; f.heavy_hdr = nullptr; f.heavy_hdr_out = nullptr; f.heavy_cap = 0;
         f.heavy_counter = reinterpret_cast<unsigned*>(ctrl + 4) + 1;
         const bool track_cost = p->mode == RT_MODE_FAST && cfg.wide != 0 && !cf.work_counters && p->schedule >= 0 && p->bounces > 0;
         const int key[5] = {w, h, p->spp, p->part_index, part_count};
         if (track_cost) {
             const size_t cap = npx / 8 + 64;
-            if (D.cost_px < npx) { // (re)allocate: the maps start empty
+            if (D.cost_px < npx) { // (re)allocate
                 CK(c, cudaStreamSynchronize(D.stream));
                 cudaFree(D.cost[0]); cudaFree(D.cost[1]); cudaFree(D.heavy_list);
                 D.cost[0] = D.cost[1] = nullptr; D.heavy_list = nullptr; D.cost_px = 0; D.cost_valid = false;
                 CK(c, cudaMalloc((void**)&D.cost[0], npx * 2)); CK(c, cudaMalloc((void**)&D.cost[1], npx * 2));
                 CK(c, cudaMalloc((void**)&D.heavy_list, cap * 4));
-                if (!D.heavy_hdr) CK(c, cudaMalloc((void**)&D.heavy_hdr, (8 + 256) * 4));
+                if (!D.heavy_hdr) CK(c, cudaMalloc((void**)&D.heavy_hdr, 8 * 4));
                 D.cost_px = npx; D.heavy_cap = cap;
+                std::memset(D.cost_key, 0, sizeof D.cost_key);
             }
-            if (std::memcmp(key, D.cost_key, sizeof key) != 0) D.cost_valid = false;
+            if (std::memcmp(key, D.cost_key, sizeof key) != 0) {
+                // another shape or partition: the history is void, and pixels this rank does not render must read 0
+                D.cost_valid = false;
+                CK(c, cudaMemsetAsync(D.cost[0], 0, npx * 2, D.stream));
+                CK(c, cudaMemsetAsync(D.cost[1], 0, npx * 2, D.stream));
+            }
             const int nxt = 1 - D.cost_cur;
-            CK(c, cudaMemsetAsync(D.cost[nxt], 0, npx * 2, D.stream)); // pixels of other parts stay 0 = never heavy
+            CK(c, cudaMemsetAsync(D.heavy_hdr + 4 * nxt, 0, 16, D.stream));
             f.cost_out = D.cost[nxt];
-            if (D.cost_valid) { f.cost_prev = D.cost[D.cost_cur]; f.heavy_list = D.heavy_list; f.heavy_hdr = D.heavy_hdr; }
+            f.heavy_hdr_out = D.heavy_hdr + 4 * nxt;
+            if (D.cost_valid) { f.cost_prev = D.cost[D.cost_cur]; f.heavy_list = D.heavy_list; f.heavy_hdr = D.heavy_hdr + 4 * D.cost_cur; f.heavy_cap = (unsigned)(npx / 8); }
         }
         f.drain_k = 0; f.drain_queue = nullptr; f.drain_cap = 0;
         f.drain_count = reinterpret_cast<unsigned*>(ctrl + 5); f.drain_next = reinterpret_cast<unsigned*>(ctrl + 6);
@@ -777,14 +762,12 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
             launches++;
         }
         if (track_cost) { // select the pixels the next frame of this shape starts with (inside this frame's timed window)
-            const unsigned cap = (unsigned)(npx / 8);
-            CK(c, cudaMemsetAsync(D.heavy_hdr, 0, (8 + 256) * 4, D.stream));
-            cost_hist_kernel<<<D.sm_count * 2, 256, 0, D.stream>>>(f.cost_out, npx, D.heavy_hdr);
-            cost_threshold_kernel<<<1, 1, 0, D.stream>>>(D.heavy_hdr, cap);
-            for (int pass = 0; pass < 3; pass++)
-                cost_compact_kernel<<<D.sm_count * 2, 256, 0, D.stream>>>(f.cost_out, w, h, pass, D.heavy_hdr, D.heavy_list, cap);
+            static const float frac = [] { const char* e = std::getenv("RT_HEAVY_FRAC"); const float v = e ? (float)std::atof(e) : 0.5f; return v > 0.f ? v : 0.5f; }();
+            const unsigned n_chunks_all = (unsigned)fa.tiles_x * (unsigned)tiles_y_of(h) * 4u;
+            cost_select_kernel<<<D.sm_count * 4, 256, 0, D.stream>>>(f.cost_out, w, h, fa.tiles_x, n_chunks_all, f.heavy_hdr_out, D.heavy_list,
+                                                                      (unsigned)(npx / 8), frac);
             CK(c, cudaGetLastError());
-            launches += 5;
+            launches += 1;
             D.cost_cur = 1 - D.cost_cur; D.cost_valid = true;
             std::memcpy(D.cost_key, key, sizeof key);
         }
