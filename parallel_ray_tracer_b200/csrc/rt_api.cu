@@ -193,8 +193,11 @@ __global__ void unpack_tiles_kernel(uchar4* __restrict__ frame, const uchar4* __
 // them in the map (bit 15).  The NEXT frame of the same shape starts with that list and skips flagged pixels in the regular
 // chunks.  Scheduling only: a pixel's bytes do not depend on when or where it is rendered.
 __global__ void cost_select_kernel(unsigned short* __restrict__ cost, int width, int height, int tiles_x, unsigned n_chunks, unsigned* __restrict__ hdr,
-                                   unsigned* __restrict__ list, unsigned cap, float frac)
+                                   unsigned* __restrict__ hdr_old, unsigned* __restrict__ list, unsigned cap, float frac)
 {
+    // the header the render kernel has just finished with becomes the next frame's output header: zero it here (saves a memset
+    // per frame; nothing reads it before the next render kernel, which only does atomicMax on it)
+    if (blockIdx.x == 0 && threadIdx.x < 4) hdr_old[threadIdx.x] = 0u;
     const unsigned mx = hdr[1];
     unsigned thr = (unsigned)((float)mx * frac);
     if (thr < 48u) thr = 48u;           // (a frame whose heaviest pixel takes a few dozen steps has no tail worth scheduling)
@@ -728,9 +731,9 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
                 D.cost_valid = false;
                 CK(c, cudaMemsetAsync(D.cost[0], 0, npx * 2, D.stream));
                 CK(c, cudaMemsetAsync(D.cost[1], 0, npx * 2, D.stream));
+                CK(c, cudaMemsetAsync(D.heavy_hdr, 0, 32, D.stream));
             }
-            const int nxt = 1 - D.cost_cur;
-            CK(c, cudaMemsetAsync(D.heavy_hdr + 4 * nxt, 0, 16, D.stream));
+            const int nxt = 1 - D.cost_cur; // (its header was zeroed by the selection kernel of the frame before last, or below)
             f.cost_out = D.cost[nxt];
             f.heavy_hdr_out = D.heavy_hdr + 4 * nxt;
             if (D.cost_valid) { f.cost_prev = D.cost[D.cost_cur]; f.heavy_list = D.heavy_list; f.heavy_hdr = D.heavy_hdr + 4 * D.cost_cur; f.heavy_cap = (unsigned)(npx / 8); }
@@ -762,10 +765,10 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
             launches++;
         }
         if (track_cost) { // select the pixels the next frame of this shape starts with (inside this frame's timed window)
-            static const float frac = [] { const char* e = std::getenv("RT_HEAVY_FRAC"); const float v = e ? (float)std::atof(e) : 0.5f; return v > 0.f ? v : 0.5f; }();
+            static const float frac = [] { const char* e = std::getenv("RT_HEAVY_FRAC"); const float v = e ? (float)std::atof(e) : 0.22f; return v > 0.f ? v : 0.22f; }();
             const unsigned n_chunks_all = (unsigned)fa.tiles_x * (unsigned)tiles_y_of(h) * 4u;
-            cost_select_kernel<<<D.sm_count * 4, 256, 0, D.stream>>>(f.cost_out, w, h, fa.tiles_x, n_chunks_all, f.heavy_hdr_out, D.heavy_list,
-                                                                      (unsigned)(npx / 8), frac);
+            cost_select_kernel<<<D.sm_count * 4, 256, 0, D.stream>>>(f.cost_out, w, h, fa.tiles_x, n_chunks_all, f.heavy_hdr_out,
+                                                                      D.heavy_hdr + 4 * D.cost_cur, D.heavy_list, (unsigned)(npx / 8), frac);
             CK(c, cudaGetLastError());
             launches += 1;
             D.cost_cur = 1 - D.cost_cur; D.cost_valid = true;
