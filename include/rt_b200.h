@@ -288,6 +288,9 @@ int rt_debug_device_array(rt_ctx* ctx, int which, void* out, size_t cap_bytes, s
 /* Roofline microbenchmark: GB/s of random 64-byte-record gathers (the shape of a node fetch, one record per
  * lane) from a working set of ws_bytes on `device` — L1-, L2- or HBM-resident depending on the size. */
 int rt_debug_gather_bandwidth(int device, size_t ws_bytes, float* gbs_out);
+/* Diagnostics: the per-pixel traversal-cost map behind rt_render_params.schedule (width*height u16 of the last fast frame: steps in
+ * bits 0-14, bit 15 = selected for the next frame's heavy list) and {entries selected, largest cost}. */
+int rt_debug_cost_map(rt_ctx* ctx, unsigned short* out, size_t n_pixels, unsigned* hdr2);
 /* Diagnostics: host -> device copy rate (GB/s) of `bytes` of pageable memory: mode 0 plain cudaMemcpy (the reference's way,
  * gpu/src/gpu.cu:143-175), 1 the library's staged copy through its pinned ring (csrc/staged_copy.h), 2 cudaMemcpy from
  * page-locked memory (the ceiling on this box). */

@@ -45,7 +45,7 @@ EXPORTS = [
     "rt_part_tile_count", "rt_packed_tiles", "rt_unpack_tiles", "rt_frame_ipc_export", "rt_frame_ipc_import",
     "rt_frame_device_ptr", "rt_write_bmp", "rt_abi_version", "rt_device_count", "rt_debug_warp_trace",
     "rt_render_async", "rt_download_async", "rt_frame_wait", "rt_host_alloc", "rt_host_free",
-    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order", "rt_scene_build_bvh_gpu", "rt_debug_gather_bandwidth", "rt_create_gpu", "rt_debug_flatten_host", "rt_debug_device_array", "rt_debug_copy_bandwidth",
+    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order", "rt_scene_build_bvh_gpu", "rt_debug_gather_bandwidth", "rt_create_gpu", "rt_debug_flatten_host", "rt_debug_device_array", "rt_debug_copy_bandwidth", "rt_debug_cost_map",
 ]
 
 
@@ -134,6 +134,8 @@ def lib() -> C.CDLL:
     L.rt_create.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(i32), i32, C.POINTER(vp)]
     L.rt_debug_flatten_host.argtypes = [C.POINTER(rt_scene_desc), i32, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(i32)]
     L.rt_create_gpu.argtypes = [vp, i32, C.POINTER(i32), i32, i32, C.POINTER(vp), C.POINTER(rt_bvh_gpu_stats)]
+    if hasattr(L, "rt_debug_cost_map"):
+        L.rt_debug_cost_map.argtypes = [vp, vp, C.c_size_t, vp]
     if hasattr(L, "rt_debug_copy_bandwidth"):
         L.rt_debug_copy_bandwidth.argtypes = [i32, C.c_size_t, i32, C.POINTER(C.c_float)]
     if hasattr(L, "rt_debug_device_array"):  # (absent from older builds loaded through RT_B200_LIB for A/B runs)
@@ -413,6 +415,14 @@ class Context:
         a = np.empty(n.value // np.dtype(dtype).itemsize, dtype)
         _check(lib().rt_debug_device_array(self._h, which, _ptr(a), a.nbytes, C.byref(n)), self._h)
         return a
+
+    def cost_map(self, width, height):
+        """Diagnostics: (per-pixel traversal steps of the last fast frame, selected mask, {entries, max})."""
+        a = np.empty(width * height, np.uint16)
+        hdr = np.zeros(2, np.uint32)
+        _check(lib().rt_debug_cost_map(self._h, _ptr(a), a.size, _ptr(hdr)), self._h)
+        a = a.reshape(height, width)
+        return a & 0x7fff, (a >> 15).astype(bool), hdr
 
     def warp_trace(self, enable=True, max_warps=8192):
         """Diagnostics: arm / read the per-warp timeline of RT_AOV_WORK renders (see rt_debug_warp_trace)."""

@@ -712,7 +712,7 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         // starts with the list selected from that frame's costs
         f.cost_out = nullptr; f.cost_prev = nullptr; f.heavy_list = nullptr; f.heavy_hdr = nullptr; f.heavy_hdr_out = nullptr; f.heavy_cap = 0;
         f.heavy_counter = reinterpret_cast<unsigned*>(ctrl + 4) + 1;
-        const bool track_cost = p->mode == RT_MODE_FAST && cfg.wide != 0 && !cf.work_counters && p->schedule >= 0 && p->bounces > 0;
+        const bool track_cost = p->mode == RT_MODE_FAST && cfg.wide != 0 && p->schedule >= 0 && p->bounces > 0;
         const int key[5] = {w, h, p->spp, p->part_index, part_count};
         if (track_cost) {
             const size_t cap = npx / 8 + 64;
@@ -1026,6 +1026,20 @@ int rt_debug_set_tile_order(rt_ctx* c, const unsigned* tiles, int n)
     if (n != D.n_tiles) return fail(c, RT_ERR_INVALID, "rt_debug_set_tile_order: tile count differs from the current tile list");
     CK(c, cudaSetDevice(D.id));
     CK(c, cudaMemcpy(D.tile_list, tiles, (size_t)n * 4, cudaMemcpyHostToDevice));
+    return RT_OK;
+}
+
+// Diagnostics: the per-pixel traversal-cost map of the last fast frame on the context's first device (W*H u16: steps in bits
+// 0-14, bit 15 = selected for the next frame's heavy list), and the selection header {entries, max cost}.
+int rt_debug_cost_map(rt_ctx* c, unsigned short* out, size_t n_pixels, unsigned* hdr2)
+{
+    if (!c || !out) return fail(c, RT_ERR_INVALID, "rt_debug_cost_map: null argument");
+    Dev& D = c->devs[0];
+    if (!D.cost_valid || n_pixels > D.cost_px) return fail(c, RT_ERR_STATE, "rt_debug_cost_map: no cost map of that size");
+    CK(c, cudaSetDevice(D.id));
+    CK(c, cudaStreamSynchronize(D.stream));
+    CK(c, cudaMemcpy(out, D.cost[D.cost_cur], n_pixels * 2, cudaMemcpyDeviceToHost));
+    if (hdr2) CK(c, cudaMemcpy(hdr2, D.heavy_hdr + 4 * D.cost_cur, 8, cudaMemcpyDeviceToHost));
     return RT_OK;
 }
 
