@@ -197,9 +197,7 @@ typedef struct rt_render_params {
      * shape (size, spp, partition) on this context starts with the pixels that were most expensive (frame sequences are
      * coherent; a wrong guess only costs time, the bytes of a pixel do not depend on when it is rendered); < 0 = chunk order only */
     int32_t   schedule;
-    /* 0 = with `schedule`, the very heaviest pixels (>= 55 % of the frame's largest cost, at most 16 per SM) are traced by the
-     * cooperative kernel — eight lanes per ray — on a second stream beside the render kernel; < 0 = off */
-    int32_t   coop;
+    int32_t   reserved;
 } rt_render_params;
 
 typedef struct rt_timing {

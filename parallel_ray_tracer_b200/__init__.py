@@ -75,7 +75,7 @@ class rt_render_params(C.Structure):
                 ("gather", C.c_int32), ("part_index", C.c_int32), ("part_count", C.c_int32),
                 ("block_threads", C.c_int32), ("ctas_per_sm", C.c_int32), ("refill_threshold", C.c_int32),
                 ("traversal", C.c_int32), ("frame_flags", C.c_int32), ("frame_slot", C.c_int32),
-                ("drain_k", C.c_int32), ("cull", C.c_int32), ("schedule", C.c_int32), ("coop", C.c_int32)]
+                ("drain_k", C.c_int32), ("cull", C.c_int32), ("schedule", C.c_int32), ("reserved", C.c_int32)]
 
 
 class rt_timing(C.Structure):

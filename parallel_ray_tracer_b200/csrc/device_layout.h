@@ -96,10 +96,6 @@ struct RtFrameArgs {
     const unsigned* heavy_hdr;     // [0] pixels the selection counted (entries = min(that, heavy_cap))
     unsigned heavy_cap;
     unsigned* heavy_hdr_out;       // [1] = max cost of this frame
-    // the very heaviest of them (heavy_hdr[2] entries) go to drain_kernel, running BESIDE the render kernel on a second stream
-    // with eight lanes per ray (set in that launch's arguments only)
-    const unsigned* coop_list;
-    unsigned coop_cap;
     unsigned* heavy_counter;       // next heavy_list entry to hand out (zeroed per frame)
     // fast build, tail of the frame: once the chunk queue is empty, a warp left with <= drain_k live pixels writes their
     // paths to drain_queue and exits; drain_kernel finishes them with eight lanes per ray (0 = off)

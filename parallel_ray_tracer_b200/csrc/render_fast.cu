@@ -28,9 +28,3 @@ cudaError_t rt_launch_drain(const RtDeviceScene& sc, const RtFrameArgs& fa, bool
     else rt_fast::drain_kernel<false><<<grid, 128, 0, st>>>(sc, fa);
     return cudaGetLastError();
 }
-
-cudaError_t rt_launch_coop(const RtDeviceScene& sc, const RtFrameArgs& fa, int sm_count, cudaStream_t st)
-{
-    rt_fast::drain_kernel<false><<<sm_count, 32, 0, st>>>(sc, fa);
-    return cudaGetLastError();
-}

@@ -19,5 +19,3 @@ cudaError_t rt_occupancy_fast(const RtLaunchCfg& cfg, int* ctas_per_sm, int* reg
 cudaError_t rt_occupancy_strict(const RtLaunchCfg& cfg, int* ctas_per_sm, int* regs);
 // the cooperative drain kernel (fast build): finishes the paths queued in fa.drain_queue; one resident wave
 cudaError_t rt_launch_drain(const RtDeviceScene& sc, const RtFrameArgs& fa, bool work_counters, int sm_count, cudaStream_t st);
-// the same kernel beside the render kernel: one 32-thread CTA per SM tracing fa.coop_list (the frame's heaviest pixels)
-cudaError_t rt_launch_coop(const RtDeviceScene& sc, const RtFrameArgs& fa, int sm_count, cudaStream_t st);

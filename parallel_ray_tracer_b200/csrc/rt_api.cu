@@ -63,12 +63,8 @@ struct Dev {
     unsigned* heavy_list = nullptr;
     size_t heavy_cap = 0;
     unsigned* heavy_hdr = nullptr;
-    unsigned* coop_list = nullptr;   // the heaviest of the heavy: traced by drain_kernel beside the render kernel
-    size_t coop_cap = 0;
-    cudaEvent_t ev_pre = nullptr, ev_coop = nullptr;
     int cost_cur = 0;
     bool cost_valid = false;
-    bool coop_built = false;         // the last selection filled the cooperative list too
     int cost_key[5] = {0, 0, 0, 0, 0}; // width, height, spp, part_index, part_count
     RtPathRec* drain_queue[RT_FRAME_SLOTS] = {}; // tail hand-off queue per frame slot (render_kernel.cuh: drain_kernel)
     size_t drain_cap[RT_FRAME_SLOTS] = {};
@@ -197,8 +193,7 @@ __global__ void unpack_tiles_kernel(uchar4* __restrict__ frame, const uchar4* __
 // them in the map (bit 15).  The NEXT frame of the same shape starts with that list and skips flagged pixels in the regular
 // chunks.  Scheduling only: a pixel's bytes do not depend on when or where it is rendered.
 __global__ void cost_select_kernel(unsigned short* __restrict__ cost, int width, int height, int tiles_x, unsigned n_chunks, unsigned* __restrict__ hdr,
-                                   unsigned* __restrict__ hdr_old, unsigned* __restrict__ list, unsigned cap, float frac,
-                                   unsigned* __restrict__ coop_list, unsigned coop_cap, float coop_frac)
+                                   unsigned* __restrict__ hdr_old, unsigned* __restrict__ list, unsigned cap, float frac)
 {
     // the header the render kernel has just finished with becomes the next frame's output header: zero it here (saves a memset
     // per frame; nothing reads it before the next render kernel, which only does atomicMax on it)
@@ -207,8 +202,6 @@ __global__ void cost_select_kernel(unsigned short* __restrict__ cost, int width,
     unsigned thr = (unsigned)((float)mx * frac);
     if (thr < 48u) thr = 48u;           // (a frame whose heaviest pixel takes a few dozen steps has no tail worth scheduling)
     if (mx < 96u) return;
-    unsigned thr_coop = (unsigned)((float)mx * coop_frac); // the very heaviest go to the cooperative kernel (hdr[2] counts them)
-    if (thr_coop < thr) thr_coop = thr;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (unsigned c = warp; c < n_chunks; c += n_warps) {   // one 8x4 chunk per warp iteration (render_kernel's pixel order)
@@ -218,19 +211,7 @@ __global__ void cost_select_kernel(unsigned short* __restrict__ cost, int width,
         const bool in = x < width && y < height;
         const size_t i = (size_t)y * width + x;
         const unsigned v = in ? cost[i] : 0u;
-        bool placed = false;
-        if (coop_cap) {
-            const bool selc = in && (v & 0x7fffu) >= thr_coop;
-            const unsigned mc = __ballot_sync(0xffffffffu, selc);
-            if (mc) {
-                unsigned cbase = 0;
-                if (lane == 0) cbase = atomicAdd(&hdr[2], (unsigned)__popc(mc));
-                cbase = __shfl_sync(0xffffffffu, cbase, 0);
-                const unsigned cpos = cbase + (unsigned)__popc(mc & ((1u << lane) - 1u));
-                if (selc && cpos < coop_cap) { coop_list[cpos] = (unsigned)x | ((unsigned)y << 16); cost[i] = (unsigned short)(v | 0x8000u); placed = true; }
-            }
-        }
-        const bool sel = in && !placed && (v & 0x7fffu) >= thr; // (a pixel the cooperative list had no room for falls through to here)
+        const bool sel = in && (v & 0x7fffu) >= thr;
         const unsigned m = __ballot_sync(0xffffffffu, sel);
         if (!m) continue;
         unsigned base = 0;
@@ -340,9 +321,7 @@ void free_dev(Dev& D)
     cudaFree(D.leaf_cnt); cudaFree(D.ctrl); cudaFree(D.tile_list); cudaFree(D.warp_trace);
     cudaFree(D.bgra); cudaFree(D.packed);
     for (int s = 0; s < RT_FRAME_SLOTS; s++) cudaFree(D.drain_queue[s]);
-    cudaFree(D.cost[0]); cudaFree(D.cost[1]); cudaFree(D.heavy_list); cudaFree(D.heavy_hdr); cudaFree(D.coop_list);
-    if (D.ev_pre) cudaEventDestroy(D.ev_pre);
-    if (D.ev_coop) cudaEventDestroy(D.ev_coop);
+    cudaFree(D.cost[0]); cudaFree(D.cost[1]); cudaFree(D.heavy_list); cudaFree(D.heavy_hdr);
     if (D.ctrl_host) cudaFreeHost(D.ctrl_host);
     for (int s = 0; s < RT_FRAME_SLOTS; s++) {
         if (D.ev0[s]) cudaEventDestroy(D.ev0[s]);
@@ -424,8 +403,6 @@ static int create_common(const rt::FlatScene& flat, rt::DeviceFlat* pre, const i
         CKC(cudaStreamCreateWithFlags(&D.aux, cudaStreamNonBlocking));
         for (int s = 0; s < RT_FRAME_SLOTS; s++) { CKC(cudaEventCreate(&D.ev0[s])); CKC(cudaEventCreate(&D.ev1[s])); CKC(cudaEventCreate(&D.ev_done[s])); }
         CKC(cudaEventCreate(&D.ev2));
-        CKC(cudaEventCreateWithFlags(&D.ev_pre, cudaEventDisableTiming));
-        CKC(cudaEventCreateWithFlags(&D.ev_coop, cudaEventDisableTiming));
         if (i == 0) {
             c->copy_stream = D.aux;
             for (int s = 0; s < RT_FRAME_SLOTS; s++) CKC(cudaEventCreateWithFlags(&c->slots[s].copy_done, cudaEventDisableTiming));
@@ -746,12 +723,9 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
                 CK(c, cudaMalloc((void**)&D.cost[0], npx * 2)); CK(c, cudaMalloc((void**)&D.cost[1], npx * 2));
                 CK(c, cudaMalloc((void**)&D.heavy_list, cap * 4));
                 if (!D.heavy_hdr) CK(c, cudaMalloc((void**)&D.heavy_hdr, 8 * 4));
-                if (!D.coop_list) { D.coop_cap = (size_t)D.sm_count * 4 * 4; CK(c, cudaMalloc((void**)&D.coop_list, D.coop_cap * 4)); } // 4 rounds of one 4-group warp per SM
                 D.cost_px = npx; D.heavy_cap = cap;
                 std::memset(D.cost_key, 0, sizeof D.cost_key);
             }
-            const bool coop_possible = p->coop >= 0 && D.nodes8 && 7 * c->depth8 + 1 <= RT_DRAIN_STACK;
-            if (D.cost_valid && D.coop_built && !coop_possible) D.cost_valid = false; // pixels flagged for a kernel that will not run
             if (std::memcmp(key, D.cost_key, sizeof key) != 0) {
                 // another shape or partition: the history is void, and pixels this rank does not render must read 0
                 D.cost_valid = false;
@@ -783,25 +757,9 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         if (S.copy_pending) CK(c, cudaStreamWaitEvent(D.stream, S.copy_done, 0));
         CK(c, cudaMemsetAsync(ctrl, 0, 8 * RT_CTRL_WORDS, D.stream));
         CK(c, cudaEventRecord(D.ev0[slot], D.stream));
-        // The very heaviest pixels of the previous frame (selection: coop list) are traced by the cooperative kernel — eight
-        // lanes per ray — BESIDE the render kernel: one 32-thread CTA per SM on the second stream, launched first so that it
-        // is resident when the render kernel's CTAs arrive (80 x 128 x 6 + 112 x 32 registers fit an SM).  Both kernels lie
-        // inside the frame's timed window; the render kernel skips the pixels (flag bit in the cost map).
-        const bool coop_on = track_cost && D.cost_valid && p->coop >= 0 && D.nodes8 && 7 * c->depth8 + 1 <= RT_DRAIN_STACK && f.heavy_hdr;
-        if (coop_on) {
-            RtFrameArgs f2 = f;
-            f2.coop_list = D.coop_list; f2.coop_cap = (unsigned)D.coop_cap;
-            f2.drain_next = reinterpret_cast<unsigned*>(ctrl + 6) + 1;
-            CK(c, cudaEventRecord(D.ev_pre, D.stream));
-            CK(c, cudaStreamWaitEvent(D.aux, D.ev_pre, 0));
-            CK(c, rt_launch_coop(sc, f2, D.sm_count, D.aux));
-            CK(c, cudaEventRecord(D.ev_coop, D.aux));
-            launches++;
-        }
         e = (p->mode == RT_MODE_STRICT) ? rt_launch_strict(sc, f, cf, D.stream) : rt_launch_fast(sc, f, cf, D.stream);
         CK(c, e);
         launches++;
-        if (coop_on) CK(c, cudaStreamWaitEvent(D.stream, D.ev_coop, 0));
         if (f.drain_k > 0) { // the paths the render kernel's warps handed off at the end of the chunk queue
             CK(c, rt_launch_drain(sc, f, cf.work_counters, D.sm_count, D.stream));
             launches++;
@@ -809,14 +767,11 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         if (track_cost) { // select the pixels the next frame of this shape starts with (inside this frame's timed window)
             static const float frac = [] { const char* e = std::getenv("RT_HEAVY_FRAC"); const float v = e ? (float)std::atof(e) : 0.22f; return v > 0.f ? v : 0.22f; }();
             const unsigned n_chunks_all = (unsigned)fa.tiles_x * (unsigned)tiles_y_of(h) * 4u;
-            static const float coop_frac = [] { const char* e = std::getenv("RT_COOP_FRAC"); const float v = e ? (float)std::atof(e) : 0.55f; return v > 0.f ? v : 0.55f; }();
-            const bool coop_next = p->coop >= 0 && D.nodes8 && 7 * c->depth8 + 1 <= RT_DRAIN_STACK;
             cost_select_kernel<<<D.sm_count * 4, 256, 0, D.stream>>>(f.cost_out, w, h, fa.tiles_x, n_chunks_all, f.heavy_hdr_out,
-                                                                      D.heavy_hdr + 4 * D.cost_cur, D.heavy_list, (unsigned)(npx / 8), frac,
-                                                                      D.coop_list, coop_next ? (unsigned)D.coop_cap : 0u, coop_frac);
+                                                                      D.heavy_hdr + 4 * D.cost_cur, D.heavy_list, (unsigned)(npx / 8), frac);
             CK(c, cudaGetLastError());
             launches += 1;
-            D.cost_cur = 1 - D.cost_cur; D.cost_valid = true; D.coop_built = coop_next;
+            D.cost_cur = 1 - D.cost_cur; D.cost_valid = true;
             std::memcpy(D.cost_key, key, sizeof key);
         }
         CK(c, cudaEventRecord(D.ev1[slot], D.stream));

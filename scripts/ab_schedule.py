@@ -14,12 +14,12 @@ for scene, w, h, parts in CASES:
     ctx = rt.Context(sc, [0])
     for rep in range(2):
         for trav in (3,):
-            for sched, coop in ((-1, -1), (0, -1), (0, 0)):
-                p = rt.default_params(width=w, height=h, traversal=trav, schedule=sched, coop=coop, part_index=0, part_count=parts)
+            for sched in (-1, 0):
+                p = rt.default_params(width=w, height=h, traversal=trav, schedule=sched, part_index=0, part_count=parts)
                 t_end = time.perf_counter() + 0.15
                 while time.perf_counter() < t_end:
                     ctx.render_frame(p)
                 ms = [ctx.render_frame(p).kernel_ms[0] for _ in range(frames)]
-                print(json.dumps({"frac": os.environ.get("RT_HEAVY_FRAC", "0.5"), "scene": scene, "w": w, "h": h, "part_count": parts, "traversal": trav, "schedule": sched, "coop": coop, "rep": rep,
+                print(json.dumps({"frac": os.environ.get("RT_HEAVY_FRAC", "0.5"), "scene": scene, "w": w, "h": h, "part_count": parts, "traversal": trav, "schedule": sched, "rep": rep,
                                   "ms": round(statistics.median(ms), 4), "min": round(min(ms), 4)}), flush=True)
     ctx.close()
