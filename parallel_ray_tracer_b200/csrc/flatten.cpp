@@ -239,9 +239,10 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
         const size_t n4 = order4.empty() ? 1 : order4.size();
         out.nodes4.resize(32 * n4);
         parallel_for(n4, [&](size_t lo, size_t hi) {
-            for (size_t k = lo; k < hi; k++) { // all slots empty by default: box at +inf, ref NONE
+            for (size_t k = lo; k < hi; k++) { // all slots empty by default: centre at +inf, half extent 0, ref NONE
                 float* q = &out.nodes4[32 * k];
-                for (int i = 0; i < 24; i++) q[i] = INFINITY;
+                for (int i = 0; i < 12; i++) q[i] = INFINITY;
+                for (int i = 12; i < 24; i++) q[i] = 0.0f;
                 const int32_t none = RT_REF_NONE_HOST;
                 for (int i = 0; i < 4; i++) std::memcpy(&q[24 + i], &none, 4);
                 for (int i = 28; i < 32; i++) q[i] = 0.0f;
@@ -249,12 +250,17 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
         });
         auto put4 = [&](float* q, int slot, const rt_bvh_node& c, int32_t ref) {
             if (ref == RT_REF_NONE_HOST) return;
-            q[0 + slot] = c.min[0]; q[4 + slot] = c.min[1]; q[8 + slot] = c.min[2];
-            q[12 + slot] = c.max[0]; q[16 + slot] = c.max[1]; q[20 + slot] = c.max[2];
+            // centre and half extent (render_kernel.cuh: box_key4); the half extent is rounded up so that
+            // [centre - half, centre + half] contains the builder's box (flatten_gpu.cu: nodes4_kernel does the same)
+            for (int a = 0; a < 3; a++) {
+                float ctr, half;
+                box_center_half(c.min[a], c.max[a], ctr, half);
+                q[4 * a + slot] = ctr; q[12 + 4 * a + slot] = half;
+            }
             std::memcpy(&q[24 + slot], &ref, 4);
         };
         if (order4.empty()) {
-            int32_t ref;
+            int32_t ref = RT_REF_NONE_HOST;
             leaf_ref(d.bvh[0], ref);
             rt_bvh_node all = d.bvh[0];
             for (int a = 0; a < 3; a++) { all.min[a] = -1e30f; all.max[a] = 1e30f; }

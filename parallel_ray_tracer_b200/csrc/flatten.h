@@ -1,6 +1,7 @@
 // flatten.h — host staging buffers of the HBM layout (device_layout.h), produced by flatten.cpp.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <memory>
 #include <string>
 #include <utility>
@@ -47,6 +48,24 @@ struct FlatScene {
         return 4 * (nodes.size() + nodes4.size() + nodes8.size() + tris.size() + shade.size() + mats.size() + lights.size() + leaf_cnt.size());
     }
 };
+
+// One axis of a 4-wide node's child box as centre and half extent (render_kernel.cuh: box_key4).  Plain IEEE
+// round-to-nearest operations only (this file is compiled without contraction), so flatten_gpu.cu's device version gives
+// the same bits: centre = mn / 2 + mx / 2, half = the larger one-sided distance, one ulp up unless it is exactly 0 —
+// a round-to-nearest difference is at most half an ulp short, so [centre - half, centre + half] contains [mn, mx].
+inline void box_center_half(float mn, float mx, float& ctr, float& half)
+{
+    ctr = mn * 0.5f + mx * 0.5f;
+    const float up = mx - ctr, dn = ctr - mn;
+    float h = up > dn ? up : dn;
+    if (h > 0.0f && h < 3.0e38f) {
+        uint32_t b;
+        std::memcpy(&b, &h, 4);
+        b += 1u;
+        std::memcpy(&h, &b, 4);
+    }
+    half = h;
+}
 
 int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err);
 void flatten_small(const rt_scene_desc& d, FlatScene& out); // mats, lights, n_lights, ambient only

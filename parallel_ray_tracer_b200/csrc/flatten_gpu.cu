@@ -129,7 +129,8 @@ __global__ void nodes4_kernel(int n_nodes, int n_tris, const rt_bvh_node* __rest
         else kids[c++] = ch;
     }
     float q[32];
-    for (int i = 0; i < 24; i++) q[i] = INFINITY;
+    for (int i = 0; i < 12; i++) q[i] = INFINITY; // empty slot: centre +inf, half extent 0
+    for (int i = 12; i < 24; i++) q[i] = 0.f;
     for (int i = 0; i < 4; i++) q[24 + i] = __int_as_float(RT_REF_NONE);
     for (int i = 28; i < 32; i++) q[i] = 0.f;
     for (int i = 0; i < c; i++) {
@@ -138,8 +139,14 @@ __global__ void nodes4_kernel(int n_nodes, int n_tris, const rt_bvh_node* __rest
         if (is_inner(kn)) ref = idx4_of[(kn.idx - 1) >> 1];
         else ref = child_ref(kn, n_tris, nullptr, flags) /* counts were recorded by nodes_kernel */;
         if (ref == RT_REF_NONE) continue;
-        q[0 + i] = kn.min[0]; q[4 + i] = kn.min[1]; q[8 + i] = kn.min[2];
-        q[12 + i] = kn.max[0]; q[16 + i] = kn.max[1]; q[20 + i] = kn.max[2];
+        for (int a = 0; a < 3; a++) { // centre and half extent, bit for bit flatten.h: box_center_half (this file: -fmad=false)
+            const float mn = kn.min[a], mx = kn.max[a];
+            const float ctr = mn * 0.5f + mx * 0.5f;
+            const float up = mx - ctr, dn = ctr - mn;
+            float h = up > dn ? up : dn;
+            if (h > 0.0f && h < 3.0e38f) h = __uint_as_float(__float_as_uint(h) + 1u);
+            q[4 * a + i] = ctr; q[12 + 4 * a + i] = h;
+        }
         q[24 + i] = __int_as_float(ref);
     }
     float4* o = out + 8 * (size_t)k4;

@@ -105,14 +105,20 @@ def test_four_wide_collapse_matches_the_two_wide_records(rt, scene):
             if ref == REF_NONE:
                 assert r4[k4, i] == REF_NONE
                 continue
-            assert np.array_equal(n4[k4, [0 + i, 4 + i, 8 + i]], mn) and np.array_equal(n4[k4, [12 + i, 16 + i, 20 + i]], mx)
+            # centre / half extent (csrc/flatten.h: box_center_half): contains the 2-wide record's box, at most 2 ulp wider
+            c, h = n4[k4, [0 + i, 4 + i, 8 + i]].astype(np.float64), n4[k4, [12 + i, 16 + i, 20 + i]].astype(np.float64)
+            lo, hi = mn.astype(np.float64), mx.astype(np.float64)
+            assert (c - h <= lo).all() and (c + h >= hi).all()
+            slack = 4 * np.spacing(np.maximum(np.maximum(np.abs(lo), np.abs(hi)), 1e-30).astype(np.float32)).astype(np.float64)
+            assert (lo - (c - h) <= slack).all() and ((c + h) - hi <= slack).all()
+            assert ((h == 0) == (lo == hi)).all()
             if ref >= 0:
                 stack.append((int(ref), int(r4[k4, i])))
             else:
                 assert r4[k4, i] == ref
             slot += 1
         for i in range(len(kids), 4):
-            assert r4[k4, i] == REF_NONE and np.isinf(n4[k4, i])
+            assert r4[k4, i] == REF_NONE and np.isinf(n4[k4, i]) and n4[k4, 12 + i] == 0   # empty slot: centre +inf, half 0
     assert visited == len(n4)
 
 
