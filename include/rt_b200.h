@@ -193,9 +193,10 @@ typedef struct rt_render_params {
     int32_t   drain_k;          /* once the chunk queue is empty, a warp left with <= drain_k live pixels hands them to the
                                    cooperative drain kernel (eight lanes per ray) */
     int32_t   cull;             /* test every 8x4-pixel chunk's ray pyramid against the top of the tree before tracing it */
-    /* fast build: 0 = heaviest pixels first — every frame records its per-pixel traversal cost, and the next frame of the same
-     * shape (size, spp, partition) on this context starts with the pixels that were most expensive (frame sequences are
-     * coherent; a wrong guess only costs time, the bytes of a pixel do not depend on when it is rendered); < 0 = chunk order only */
+    /* fast build: 0 = heaviest tiles first — every frame records its per-pixel traversal cost, and the next frame of the same
+     * shape (size, spp, partition) on this context renders its 16x8 tiles in the order of their most expensive pixel (frame
+     * sequences are coherent; a wrong guess only costs time, the bytes of a pixel do not depend on when it is rendered);
+     * < 0 = spatial tile order only */
     int32_t   schedule;
     int32_t   reserved;
 } rt_render_params;
@@ -288,9 +289,14 @@ int rt_debug_device_array(rt_ctx* ctx, int which, void* out, size_t cap_bytes, s
 /* Roofline microbenchmark: GB/s of random 64-byte-record gathers (the shape of a node fetch, one record per
  * lane) from a working set of ws_bytes on `device` — L1-, L2- or HBM-resident depending on the size. */
 int rt_debug_gather_bandwidth(int device, size_t ws_bytes, float* gbs_out);
-/* Diagnostics: the per-pixel traversal-cost map behind rt_render_params.schedule (width*height u16 of the last fast frame: steps in
- * bits 0-14, bit 15 = selected for the next frame's heavy list) and {entries selected, largest cost}. */
+/* Diagnostics: the per-pixel traversal-cost map behind rt_render_params.schedule (width*height u16 of the last fast frame on the
+ * first device: traversal steps, saturating; pixels of other ranks' tiles are undefined) and hdr2 = {tiles ordered ahead of the
+ * cheapest class, tiles of this rank}. */
 int rt_debug_cost_map(rt_ctx* ctx, unsigned short* out, size_t n_pixels, unsigned* hdr2);
+/* Diagnostics: the first device's tile list (tile = ty * tiles_x + tx of 16x8-pixel tiles) — which = 0: the partition's list in
+ * its base order, 1: the order the next frame of the same shape will render in (heaviest tiles first; RT_ERR_STATE if there is
+ * no cost history).  Writes min(n, cap) entries, *n_out = n. */
+int rt_debug_tile_order(rt_ctx* ctx, int which, unsigned* out, int cap, int* n_out);
 /* Diagnostics: host -> device copy rate (GB/s) of `bytes` of pageable memory: mode 0 plain cudaMemcpy (the reference's way,
  * gpu/src/gpu.cu:143-175), 1 the library's staged copy through its pinned ring (csrc/staged_copy.h), 2 cudaMemcpy from
  * page-locked memory (the ceiling on this box). */

@@ -45,7 +45,7 @@ EXPORTS = [
     "rt_part_tile_count", "rt_packed_tiles", "rt_unpack_tiles", "rt_frame_ipc_export", "rt_frame_ipc_import",
     "rt_frame_device_ptr", "rt_write_bmp", "rt_abi_version", "rt_device_count", "rt_debug_warp_trace",
     "rt_render_async", "rt_download_async", "rt_frame_wait", "rt_host_alloc", "rt_host_free",
-    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order", "rt_scene_build_bvh_gpu", "rt_debug_gather_bandwidth", "rt_create_gpu", "rt_debug_flatten_host", "rt_debug_device_array", "rt_debug_copy_bandwidth", "rt_debug_cost_map",
+    "rt_frame_ipc_export_slot", "rt_frame_ipc_import_slot", "rt_write_bmp_bottom_up", "rt_debug_set_tile_order", "rt_scene_build_bvh_gpu", "rt_debug_gather_bandwidth", "rt_create_gpu", "rt_debug_flatten_host", "rt_debug_device_array", "rt_debug_copy_bandwidth", "rt_debug_cost_map", "rt_debug_tile_order",
 ]
 
 
@@ -136,6 +136,8 @@ def lib() -> C.CDLL:
     L.rt_create_gpu.argtypes = [vp, i32, C.POINTER(i32), i32, i32, C.POINTER(vp), C.POINTER(rt_bvh_gpu_stats)]
     if hasattr(L, "rt_debug_cost_map"):
         L.rt_debug_cost_map.argtypes = [vp, vp, C.c_size_t, vp]
+    if hasattr(L, "rt_debug_tile_order"):
+        L.rt_debug_tile_order.argtypes = [vp, C.c_int, vp, C.c_int, vp]
     if hasattr(L, "rt_debug_copy_bandwidth"):
         L.rt_debug_copy_bandwidth.argtypes = [i32, C.c_size_t, i32, C.POINTER(C.c_float)]
     if hasattr(L, "rt_debug_device_array"):  # (absent from older builds loaded through RT_B200_LIB for A/B runs)
@@ -417,12 +419,18 @@ class Context:
         return a
 
     def cost_map(self, width, height):
-        """Diagnostics: (per-pixel traversal steps of the last fast frame, selected mask, {entries, max})."""
+        """Diagnostics: (per-pixel traversal steps of the last fast frame, {tiles ordered ahead of the cheapest class, tiles})."""
         a = np.empty(width * height, np.uint16)
         hdr = np.zeros(2, np.uint32)
         _check(lib().rt_debug_cost_map(self._h, _ptr(a), a.size, _ptr(hdr)), self._h)
-        a = a.reshape(height, width)
-        return a & 0x7fff, (a >> 15).astype(bool), hdr
+        return a.reshape(height, width), hdr
+
+    def tile_order(self, sorted=False, cap=1 << 22):
+        """Diagnostics: the first device's tile list in base order, or in the cost order the next frame will render in."""
+        out = np.empty(cap, np.uint32)
+        n = C.c_int(0)
+        _check(lib().rt_debug_tile_order(self._h, int(bool(sorted)), _ptr(out), cap, C.byref(n)), self._h)
+        return out[:min(n.value, cap)].copy()
 
     def warp_trace(self, enable=True, max_warps=8192):
         """Diagnostics: arm / read the per-warp timeline of RT_AOV_WORK renders (see rt_debug_warp_trace)."""

@@ -87,16 +87,9 @@ struct RtFrameArgs {
     unsigned n_sms;
     int   refill_threshold;
     int   cull;                    // fast build: test every chunk's ray pyramid against the top of nodes8 first (needs sc.nodes8)
-    // fast build, heaviest pixels first (rt_api.cu: cost_select_kernel).  cost_out receives every pixel's traversal steps (15
-    // bits) and heavy_hdr_out[1] their maximum; heavy_list holds the pixels (x | y << 16) the selection took from the PREVIOUS
-    // frame of this shape — flagged with bit 15 in cost_prev — which the warps render before the regular chunks and skip there.
+    // fast build, heaviest tiles first (rt_api.cu: tile_class_kernel): receives every rendered pixel's traversal steps (u16,
+    // saturating); the next frame's tile_list is ordered by them.  Null = not tracked.
     unsigned short* cost_out;
-    const unsigned short* cost_prev;
-    const unsigned* heavy_list;
-    const unsigned* heavy_hdr;     // [0] pixels the selection counted (entries = min(that, heavy_cap))
-    unsigned heavy_cap;
-    unsigned* heavy_hdr_out;       // [1] = max cost of this frame
-    unsigned* heavy_counter;       // next heavy_list entry to hand out (zeroed per frame)
     // fast build, tail of the frame: once the chunk queue is empty, a warp left with <= drain_k live pixels writes their
     // paths to drain_queue and exits; drain_kernel finishes them with eight lanes per ray (0 = off)
     int   drain_k;

@@ -49,6 +49,7 @@ struct Dev {
     // the layout of packed tile buffers
     unsigned* tile_list = nullptr;
     int n_tiles = 0;
+    int tile_epoch = 0, tile_epoch_seen = -1; // bumped whenever tile_list changes: an order made from another list is void
     size_t tile_cap = 0;
     // local frame of devices > 0 in PEER_COPY mode (the assembled frames live in rt_ctx::slots, on device 0)
     uchar4* bgra = nullptr;
@@ -56,13 +57,16 @@ struct Dev {
     uchar4* packed = nullptr; // packed tiles (gather paths)
     size_t packed_px = 0;
     bool peer_to_0 = false;
-    // heaviest-pixels-first scheduling (fast build): per-pixel traversal cost of the last two frames (ping-pong; bit 15 = "in the
-    // list"), the list selected from the newer one, two headers {entries, largest cost, -, -} (ping-pong), and what it belongs to
-    unsigned short* cost[2] = {nullptr, nullptr};
+    // heaviest-tiles-first scheduling (fast build): per-pixel traversal cost of the last frame, the tile list ordered by it
+    // (what the next frame of the same shape renders from), per-tile classes, two count/cursor headers (ping-pong), per-block
+    // class counts of the ordering kernels, and what all of it belongs to
+    unsigned short* cost = nullptr;
     size_t cost_px = 0;
-    unsigned* heavy_list = nullptr;
-    size_t heavy_cap = 0;
-    unsigned* heavy_hdr = nullptr;
+    unsigned* tile_sorted = nullptr;
+    unsigned char* tile_cls = nullptr;
+    size_t sorted_cap = 0;
+    unsigned* cost_hdr = nullptr;
+    unsigned* cost_blk = nullptr;
     int cost_cur = 0;
     bool cost_valid = false;
     int cost_key[5] = {0, 0, 0, 0, 0}; // width, height, spp, part_index, part_count
@@ -184,41 +188,104 @@ __global__ void unpack_tiles_kernel(uchar4* __restrict__ frame, const uchar4* __
     frame[(size_t)y * width + x] = gathered[(size_t)owner * stride_px + (size_t)li * RT_TILE_PIXELS + p];
 }
 
-// ------------------------------------------------------------------ heaviest pixels first
+// ------------------------------------------------------------------ heaviest tiles first
 // The frame time of a small frame is the dependent chain of its heaviest pixels (8 rays x hundreds of traversal steps) counted
 // from the moment they START (profiles/r02_notes.md §6): a heavy pixel fetched when the chunk queue is nearly empty ends the frame
-// half a millisecond later, alone on its SM.  Frame sequences are coherent, so the kernel records every pixel's traversal steps
-// (RtFrameArgs::cost_out, 15 bits) and the largest of them (heavy_hdr_out[1]); the kernel below then lists the pixels that took at
-// least a fraction of that maximum — walking the frame chunk by chunk, so that 32 consecutive entries are neighbours — and flags
-// them in the map (bit 15).  The NEXT frame of the same shape starts with that list and skips flagged pixels in the regular
-// chunks.  Scheduling only: a pixel's bytes do not depend on when or where it is rendered.
-__global__ void cost_select_kernel(unsigned short* __restrict__ cost, int width, int height, int tiles_x, unsigned n_chunks, unsigned* __restrict__ hdr,
-                                   unsigned* __restrict__ hdr_old, unsigned* __restrict__ list, unsigned cap, float frac)
+// a fifth of a millisecond later, alone on its SM.  Frame sequences are coherent, so the render kernel records every pixel's
+// traversal steps (RtFrameArgs::cost_out) and the two kernels below order the NEXT frame's tile list by them: tiles sorted by the
+// cost CLASS of their heaviest pixel (half octaves: < 32 steps, 32-47, 48-63, 64-95, ...), heaviest class first, original
+// (spatial) order within a class — longest-processing-time-first scheduling by counting sort.  Tiles stay whole (16x8 pixels,
+// four 8x4 chunks), so warps keep rendering neighbouring pixels.  Scheduling only: a pixel's bytes do not depend on when or
+// where it is rendered.
+//   header (RT_COST_HDR words, two of them, ping-pong): [k] tiles of class k.  Blocks take contiguous ranges of the tile
+//   list; pass 1 leaves every tile's class in `cls`, every block's class counts in `blk` and the totals in the header; pass 2
+//   places every block's tiles of a class behind those of the blocks before it — a stable counting sort.
+constexpr int RT_COST_CLASSES = 21;
+constexpr int RT_COST_HDR = 64;
+constexpr int RT_COST_BLOCK = 256;
+
+__device__ __forceinline__ int cost_class(unsigned v)
 {
-    // the header the render kernel has just finished with becomes the next frame's output header: zero it here (saves a memset
-    // per frame; nothing reads it before the next render kernel, which only does atomicMax on it)
-    if (blockIdx.x == 0 && threadIdx.x < 4) hdr_old[threadIdx.x] = 0u;
-    const unsigned mx = hdr[1];
-    unsigned thr = (unsigned)((float)mx * frac);
-    if (thr < 48u) thr = 48u;           // (a frame whose heaviest pixel takes a few dozen steps has no tail worth scheduling)
-    if (mx < 96u) return;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned c = warp; c < n_chunks; c += n_warps) {   // one 8x4 chunk per warp iteration (render_kernel's pixel order)
-        const unsigned tile = c >> 2, b = c & 3u;
-        const int x = (int)(tile % (unsigned)tiles_x) * RT_TILE_W + (int)((b & 1u) << 3) + (int)(lane & 7u);
-        const int y = (int)(tile / (unsigned)tiles_x) * RT_TILE_H + (int)((b >> 1) << 2) + (int)(lane >> 3);
-        const bool in = x < width && y < height;
-        const size_t i = (size_t)y * width + x;
-        const unsigned v = in ? cost[i] : 0u;
-        const bool sel = in && (v & 0x7fffu) >= thr;
-        const unsigned m = __ballot_sync(0xffffffffu, sel);
-        if (!m) continue;
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&hdr[0], (unsigned)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const unsigned pos = base + (unsigned)__popc(m & ((1u << lane) - 1u));
-        if (sel && pos < cap) { list[pos] = (unsigned)x | ((unsigned)y << 16); cost[i] = (unsigned short)(v | 0x8000u); }
+    if (v < 32u) return 0;
+    const int e = 31 - __clz(v);                 // 5 .. 15
+    return 1 + 2 * (e - 5) + (int)((v >> (e - 1)) & 1u); // <= 20 for v <= 49151; the map saturates at 65535
+}
+
+__global__ void __launch_bounds__(RT_COST_BLOCK) tile_class_kernel(const unsigned short* __restrict__ cost, int width, int height, int tiles_x,
+                                                                    const unsigned* __restrict__ tile_list, int n_tiles, unsigned char* __restrict__ cls,
+                                                                    unsigned* __restrict__ hdr, unsigned* __restrict__ hdr_old, unsigned* __restrict__ blk)
+{
+    __shared__ unsigned s_cnt[RT_COST_CLASSES];
+    // the header the placement kernel of the previous frame has finished with becomes the next frame's: zero it here (saves
+    // a memset per frame; nothing touches it before the next frame's kernels)
+    if (blockIdx.x == 0 && threadIdx.x < RT_COST_HDR) hdr_old[threadIdx.x] = 0u;
+    if (threadIdx.x < RT_COST_CLASSES) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, per = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int k0 = blockIdx.x * per, k1 = min(k0 + per, n_tiles);
+    for (int k = k0 + warp; k < k1; k += RT_COST_BLOCK / 32) { // one 16x8 tile per warp: lane = row (lane >> 2), 4 columns from (lane & 3) * 4
+        const unsigned tile = tile_list[k];
+        const int y = (int)(tile / (unsigned)tiles_x) * RT_TILE_H + (lane >> 2), x0 = (int)(tile % (unsigned)tiles_x) * RT_TILE_W + ((lane & 3) << 2);
+        unsigned m = 0;
+        if (y < height)
+            for (int j = 0; j < 4; j++)
+                if (x0 + j < width) m = max(m, (unsigned)cost[(size_t)y * width + x0 + j]);
+        m = __reduce_max_sync(0xffffffffu, m);
+        if (lane == 0) {
+            const int c = min(cost_class(m), RT_COST_CLASSES - 1);
+            cls[k] = (unsigned char)c;
+            atomicAdd(&s_cnt[c], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < RT_COST_CLASSES) {
+        const unsigned n = s_cnt[threadIdx.x];
+        blk[blockIdx.x * RT_COST_CLASSES + threadIdx.x] = n;
+        if (n) atomicAdd(&hdr[threadIdx.x], n);
+    }
+}
+
+__global__ void __launch_bounds__(RT_COST_BLOCK) tile_place_kernel(const unsigned* __restrict__ tile_list, int n_tiles, const unsigned char* __restrict__ cls,
+                                                                    const unsigned* __restrict__ hdr, const unsigned* __restrict__ blk, unsigned* __restrict__ sorted)
+{
+    __shared__ unsigned s_base[RT_COST_CLASSES];
+    __shared__ unsigned s_wcnt[RT_COST_BLOCK / 32][RT_COST_CLASSES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, per = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int k0 = blockIdx.x * per, k1 = min(k0 + per, n_tiles);
+    // where this block's tiles of class c go: after all tiles of heavier classes and after this class's tiles of the blocks
+    // before this one (their counts summed here: no cursor, the order is the list's order and the same on every run)
+    if (threadIdx.x < RT_COST_CLASSES) s_base[threadIdx.x] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)blockIdx.x * RT_COST_CLASSES; i += RT_COST_BLOCK) {
+        const unsigned n = blk[i];
+        if (n) atomicAdd(&s_base[i % RT_COST_CLASSES], n);
+    }
+    __syncthreads();
+    if (threadIdx.x < RT_COST_CLASSES) {
+        unsigned above = 0;
+        for (int j = threadIdx.x + 1; j < RT_COST_CLASSES; j++) above += hdr[j];   // heavier classes come first
+        s_base[threadIdx.x] += above;
+    }
+    for (int b = k0; b < k1; b += RT_COST_BLOCK) { // 256 list entries at a time, kept in list order within a class
+        for (int i = threadIdx.x; i < (RT_COST_BLOCK / 32) * RT_COST_CLASSES; i += RT_COST_BLOCK) (&s_wcnt[0][0])[i] = 0u;
+        __syncthreads();
+        const int k = b + threadIdx.x;
+        const int c = k < k1 ? (int)cls[k] : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, c);
+        if (c >= 0 && lane == __ffs(peers) - 1) s_wcnt[warp][c] = (unsigned)__popc(peers);
+        __syncthreads();
+        if (c >= 0) {
+            unsigned pos = s_base[c] + (unsigned)__popc(peers & ((1u << lane) - 1u));
+            for (int w = 0; w < warp; w++) pos += s_wcnt[w][c];
+            sorted[pos] = tile_list[k];
+        }
+        __syncthreads();
+        if (threadIdx.x < RT_COST_CLASSES) {
+            unsigned n = 0;
+            for (int w = 0; w < RT_COST_BLOCK / 32; w++) n += s_wcnt[w][threadIdx.x];
+            s_base[threadIdx.x] += n;
+        }
+        __syncthreads();
     }
 }
 
@@ -291,6 +358,7 @@ int setup_tiles(rt_ctx* c, int w, int h, int part_index, int part_count)
         if (!tl.empty()) CK(c, cudaMemcpyAsync(D.tile_list, tl.data(), tl.size() * 4, cudaMemcpyHostToDevice, D.stream));
         CK(c, cudaStreamSynchronize(D.stream)); // tl is reused by the next iteration
         D.n_tiles = (int)tl.size();
+        D.tile_epoch++;
     }
     c->tl_w = w; c->tl_h = h; c->tl_parts = parts; c->tl_index = part_index;
     return RT_OK;
@@ -321,7 +389,7 @@ void free_dev(Dev& D)
     cudaFree(D.leaf_cnt); cudaFree(D.ctrl); cudaFree(D.tile_list); cudaFree(D.warp_trace);
     cudaFree(D.bgra); cudaFree(D.packed);
     for (int s = 0; s < RT_FRAME_SLOTS; s++) cudaFree(D.drain_queue[s]);
-    cudaFree(D.cost[0]); cudaFree(D.cost[1]); cudaFree(D.heavy_list); cudaFree(D.heavy_hdr);
+    cudaFree(D.cost); cudaFree(D.tile_sorted); cudaFree(D.tile_cls); cudaFree(D.cost_hdr); cudaFree(D.cost_blk);
     if (D.ctrl_host) cudaFreeHost(D.ctrl_host);
     for (int s = 0; s < RT_FRAME_SLOTS; s++) {
         if (D.ev0[s]) cudaEventDestroy(D.ev0[s]);
@@ -708,35 +776,32 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         const int warps_needed = (D.n_tiles * (RT_TILE_PIXELS / 32) + (cf.block_threads / 32) - 1) / (cf.block_threads / 32);
         if (warps_needed < cf.grid) cf.grid = std::max(warps_needed, 1);
 
-        // heaviest pixels first: this frame records costs into the other buffer and, when the previous frame had this shape,
-        // starts with the list selected from that frame's costs
-        f.cost_out = nullptr; f.cost_prev = nullptr; f.heavy_list = nullptr; f.heavy_hdr = nullptr; f.heavy_hdr_out = nullptr; f.heavy_cap = 0;
-        f.heavy_counter = reinterpret_cast<unsigned*>(ctrl + 4) + 1;
-        const bool track_cost = p->mode == RT_MODE_FAST && cfg.wide != 0 && p->schedule >= 0 && p->bounces > 0;
+        // heaviest tiles first: this frame records per-pixel costs and, when the previous frame had this shape, renders the
+        // tiles in the order made from that frame's costs
+        f.cost_out = nullptr;
+        const bool track_cost = p->mode == RT_MODE_FAST && cfg.wide != 0 && p->schedule >= 0 && p->bounces > 0 && D.n_tiles > 0;
         const int key[5] = {w, h, p->spp, p->part_index, part_count};
         if (track_cost) {
-            const size_t cap = npx / 8 + 64;
-            if (D.cost_px < npx) { // (re)allocate
+            if (D.cost_px < npx || D.sorted_cap < (size_t)D.n_tiles) { // (re)allocate
                 CK(c, cudaStreamSynchronize(D.stream));
-                cudaFree(D.cost[0]); cudaFree(D.cost[1]); cudaFree(D.heavy_list);
-                D.cost[0] = D.cost[1] = nullptr; D.heavy_list = nullptr; D.cost_px = 0; D.cost_valid = false;
-                CK(c, cudaMalloc((void**)&D.cost[0], npx * 2)); CK(c, cudaMalloc((void**)&D.cost[1], npx * 2));
-                CK(c, cudaMalloc((void**)&D.heavy_list, cap * 4));
-                if (!D.heavy_hdr) CK(c, cudaMalloc((void**)&D.heavy_hdr, 8 * 4));
-                D.cost_px = npx; D.heavy_cap = cap;
+                cudaFree(D.cost); cudaFree(D.tile_sorted); cudaFree(D.tile_cls);
+                D.cost = nullptr; D.tile_sorted = nullptr; D.tile_cls = nullptr; D.cost_px = 0; D.sorted_cap = 0; D.cost_valid = false;
+                CK(c, cudaMalloc((void**)&D.cost, npx * 2));
+                CK(c, cudaMalloc((void**)&D.tile_sorted, (size_t)D.n_tiles * 4)); CK(c, cudaMalloc((void**)&D.tile_cls, (size_t)D.n_tiles));
+                if (!D.cost_hdr) {
+                    CK(c, cudaMalloc((void**)&D.cost_hdr, 2 * RT_COST_HDR * 4));
+                    CK(c, cudaMalloc((void**)&D.cost_blk, (size_t)D.sm_count * 4 * RT_COST_CLASSES * 4));
+                }
+                D.cost_px = npx; D.sorted_cap = (size_t)D.n_tiles;
                 std::memset(D.cost_key, 0, sizeof D.cost_key);
             }
-            if (std::memcmp(key, D.cost_key, sizeof key) != 0) {
-                // another shape or partition: the history is void, and pixels this rank does not render must read 0
-                D.cost_valid = false;
-                CK(c, cudaMemsetAsync(D.cost[0], 0, npx * 2, D.stream));
-                CK(c, cudaMemsetAsync(D.cost[1], 0, npx * 2, D.stream));
-                CK(c, cudaMemsetAsync(D.heavy_hdr, 0, 32, D.stream));
+            if (std::memcmp(key, D.cost_key, sizeof key) != 0 || D.tile_epoch_seen != D.tile_epoch) {
+                // another shape, partition or tile list: the history is void (pixels this rank does not render are never read)
+                D.cost_valid = false; D.tile_epoch_seen = D.tile_epoch;
+                CK(c, cudaMemsetAsync(D.cost_hdr, 0, 2 * RT_COST_HDR * 4, D.stream));
             }
-            const int nxt = 1 - D.cost_cur; // (its header was zeroed by the selection kernel of the frame before last, or below)
-            f.cost_out = D.cost[nxt];
-            f.heavy_hdr_out = D.heavy_hdr + 4 * nxt;
-            if (D.cost_valid) { f.cost_prev = D.cost[D.cost_cur]; f.heavy_list = D.heavy_list; f.heavy_hdr = D.heavy_hdr + 4 * D.cost_cur; f.heavy_cap = (unsigned)(npx / 8); }
+            f.cost_out = D.cost;
+            if (D.cost_valid) f.tile_list = D.tile_sorted;
         }
         f.drain_k = 0; f.drain_queue = nullptr; f.drain_cap = 0;
         f.drain_count = reinterpret_cast<unsigned*>(ctrl + 5); f.drain_next = reinterpret_cast<unsigned*>(ctrl + 6);
@@ -764,13 +829,14 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
             CK(c, rt_launch_drain(sc, f, cf.work_counters, D.sm_count, D.stream));
             launches++;
         }
-        if (track_cost) { // select the pixels the next frame of this shape starts with (inside this frame's timed window)
-            static const float frac = [] { const char* e = std::getenv("RT_HEAVY_FRAC"); const float v = e ? (float)std::atof(e) : 0.22f; return v > 0.f ? v : 0.22f; }();
-            const unsigned n_chunks_all = (unsigned)fa.tiles_x * (unsigned)tiles_y_of(h) * 4u;
-            cost_select_kernel<<<D.sm_count * 4, 256, 0, D.stream>>>(f.cost_out, w, h, fa.tiles_x, n_chunks_all, f.heavy_hdr_out,
-                                                                      D.heavy_hdr + 4 * D.cost_cur, D.heavy_list, (unsigned)(npx / 8), frac);
+        if (track_cost) { // order the tiles for the next frame of this shape (inside this frame's timed window)
+            const int nb = std::min(D.sm_count * 4, (D.n_tiles + 7) / 8);
+            unsigned* const hdr = D.cost_hdr + RT_COST_HDR * D.cost_cur;
+            tile_class_kernel<<<nb, RT_COST_BLOCK, 0, D.stream>>>(D.cost, w, h, fa.tiles_x, D.tile_list, D.n_tiles, D.tile_cls, hdr,
+                                                                  D.cost_hdr + RT_COST_HDR * (1 - D.cost_cur), D.cost_blk);
+            tile_place_kernel<<<nb, RT_COST_BLOCK, 0, D.stream>>>(D.tile_list, D.n_tiles, D.tile_cls, hdr, D.cost_blk, D.tile_sorted);
             CK(c, cudaGetLastError());
-            launches += 1;
+            launches += 2;
             D.cost_cur = 1 - D.cost_cur; D.cost_valid = true;
             std::memcpy(D.cost_key, key, sizeof key);
         }
@@ -1026,11 +1092,12 @@ int rt_debug_set_tile_order(rt_ctx* c, const unsigned* tiles, int n)
     if (n != D.n_tiles) return fail(c, RT_ERR_INVALID, "rt_debug_set_tile_order: tile count differs from the current tile list");
     CK(c, cudaSetDevice(D.id));
     CK(c, cudaMemcpy(D.tile_list, tiles, (size_t)n * 4, cudaMemcpyHostToDevice));
+    D.tile_epoch++;
     return RT_OK;
 }
 
-// Diagnostics: the per-pixel traversal-cost map of the last fast frame on the context's first device (W*H u16: steps in bits
-// 0-14, bit 15 = selected for the next frame's heavy list), and the selection header {entries, max cost}.
+// Diagnostics: the per-pixel traversal-cost map of the last fast frame on the context's first device (W*H u16 steps,
+// saturating; pixels another rank renders are undefined), and hdr2 = {tiles ordered ahead of the cheap class, tiles in all}.
 int rt_debug_cost_map(rt_ctx* c, unsigned short* out, size_t n_pixels, unsigned* hdr2)
 {
     if (!c || !out) return fail(c, RT_ERR_INVALID, "rt_debug_cost_map: null argument");
@@ -1038,8 +1105,26 @@ int rt_debug_cost_map(rt_ctx* c, unsigned short* out, size_t n_pixels, unsigned*
     if (!D.cost_valid || n_pixels > D.cost_px) return fail(c, RT_ERR_STATE, "rt_debug_cost_map: no cost map of that size");
     CK(c, cudaSetDevice(D.id));
     CK(c, cudaStreamSynchronize(D.stream));
-    CK(c, cudaMemcpy(out, D.cost[D.cost_cur], n_pixels * 2, cudaMemcpyDeviceToHost));
-    if (hdr2) CK(c, cudaMemcpy(hdr2, D.heavy_hdr + 4 * D.cost_cur, 8, cudaMemcpyDeviceToHost));
+    CK(c, cudaMemcpy(out, D.cost, n_pixels * 2, cudaMemcpyDeviceToHost));
+    if (hdr2) {
+        unsigned h[RT_COST_CLASSES];
+        CK(c, cudaMemcpy(h, D.cost_hdr + RT_COST_HDR * (1 - D.cost_cur), sizeof h, cudaMemcpyDeviceToHost)); // the last frame's header
+        hdr2[0] = 0; hdr2[1] = 0;
+        for (int k = 0; k < RT_COST_CLASSES; k++) { hdr2[1] += h[k]; if (k) hdr2[0] += h[k]; }
+    }
+    return RT_OK;
+}
+
+int rt_debug_tile_order(rt_ctx* c, int which, unsigned* out, int cap, int* n_out)
+{
+    if (!c || !out || !n_out || cap < 0 || which < 0 || which > 1) return fail(c, RT_ERR_INVALID, "rt_debug_tile_order: bad argument");
+    Dev& D = c->devs[0];
+    if (which == 1 && (!D.cost_valid || D.tile_epoch_seen != D.tile_epoch)) return fail(c, RT_ERR_STATE, "rt_debug_tile_order: no cost history");
+    CK(c, cudaSetDevice(D.id));
+    CK(c, cudaStreamSynchronize(D.stream));
+    *n_out = D.n_tiles;
+    const int n = std::min(cap, D.n_tiles);
+    if (n > 0) CK(c, cudaMemcpy(out, which ? D.tile_sorted : D.tile_list, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return RT_OK;
 }
 

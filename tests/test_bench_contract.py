@@ -36,7 +36,7 @@ def test_b200_arm_line(rt):
     assert BASE_KEYS <= set(d) and d["metric"] == "Mrays/s" and d["n_gpus"] == 1 and d["steps"] == 4 and d["warmup"] >= 3
     assert d["config"]["workload"] == "car_only_1080p" and "model" not in d["config"] and d["dtype"] == "f32" and d["vs_baseline"] is None
     assert d["value"] > 500 and abs(d["value"] - d["rays_per_frame"] / d["ms_per_step"] / 1e3) < 1e-6 * d["value"]
-    assert d["gpu_launches"] == 4 * 2  # per timed frame: the render kernel + the kernel that selects the next frame's heavy pixels
+    assert d["gpu_launches"] == 4 * 3  # per timed frame: the render kernel + the two kernels that order the next frame's tiles
     e = d["e2e"]
     assert e["unit"] == d["unit"] and e["value"] > 0 and e["d2h_bytes_per_step"] == 1920 * 1080 * 4 and e["h2d_bytes_per_step"] > 0
     r = d["roofline"]

@@ -1,7 +1,7 @@
-"""Heaviest-pixels-first scheduling (rt_render_params.schedule = 0, the default of the fast build on the wide trees): every
-frame records its per-pixel traversal cost and the next frame of the same shape starts with the most expensive pixels.
-It is scheduling only — the bytes of a pixel must not depend on when or by which warp it is rendered, whether the cost map
-is fresh, stale (the camera moved) or absent (first frame, new resolution, new partition)."""
+"""Heaviest-tiles-first scheduling (rt_render_params.schedule = 0, the default of the fast build on the wide trees): every
+frame records its per-pixel traversal cost and the next frame of the same shape renders its tiles in the order of their most
+expensive pixel.  It is scheduling only — the bytes of a pixel must not depend on when or by which warp it is rendered, whether
+the cost map is fresh, stale (the camera moved) or absent (first frame, new resolution, new partition)."""
 import numpy as np
 import pytest
 
@@ -39,10 +39,26 @@ def test_heavy_first_frames_equal_chunk_order_frames(rt, gpu_scenes, scene, trav
     w, h = 960, 540
     plain = render(rt, ctx, w, h, traversal=traversal, schedule=-1)
     assert plain["launches"] == 1
-    for k in range(3):                 # frame 0 has no history, frames 1-2 start with the heavy list
+    for k in range(3):                 # frame 0 has no history, frames 1-2 render in cost order
         got = render(rt, ctx, w, h, traversal=traversal)
-        assert got["launches"] == 2    # render kernel + the kernel that selects the next frame's heavy pixels
+        assert got["launches"] == 3    # render kernel + the two kernels that order the next frame's tiles
         assert same(got, plain), (scene, traversal, k)
+    # the order the next frame will use: a permutation of the tile list, heaviest class first, list order within a class
+    base, order = ctx.tile_order(), ctx.tile_order(sorted=True)
+    cost, hdr = ctx.cost_map(w, h)
+    assert len(order) == len(base) == ((w + 15) // 16) * ((h + 7) // 8) == hdr[1]
+    assert np.array_equal(np.sort(order), np.sort(base))
+    tx = (w + 15) // 16
+    pad = np.zeros((((h + 7) // 8) * 8, tx * 16), np.int64); pad[:h, :w] = cost
+    tmax = pad.reshape(-1, 8, tx, 16).max(axis=(1, 3)).reshape(-1)
+    v = np.maximum(tmax, 32)
+    e = np.floor(np.log2(v)).astype(np.int64)                         # csrc/rt_api.cu: cost_class — half octaves from 32 steps
+    cls = np.where(tmax >= 32, np.minimum(1 + 2 * (e - 5) + ((v >> (e - 1)) & 1), 20), 0)
+    assert (np.diff(cls[order]) <= 0).all() and hdr[0] == (cls > 0).sum()
+    pos = {int(t): i for i, t in enumerate(base)}
+    for c in np.unique(cls):
+        seq = [pos[int(t)] for t in order[cls[order] == c]]
+        assert seq == sorted(seq), c
     # stale map: the camera moved between the frame that produced the map and the frame that uses it
     cam = (O.DEFAULT_CAM_POS, (O.DEFAULT_CAM_ROT[0], 0.0, 0.35), O.DEFAULT_FOV)
     moved = render(rt, ctx, w, h, traversal=traversal, cam=cam)
