@@ -256,9 +256,10 @@ __global__ void __launch_bounds__(RT_COST_BLOCK) tile_place_kernel(const unsigne
     // before this one (their counts summed here: no cursor, the order is the list's order and the same on every run)
     if (threadIdx.x < RT_COST_CLASSES) s_base[threadIdx.x] = 0u;
     __syncthreads();
-    for (int i = threadIdx.x; i < (int)blockIdx.x * RT_COST_CLASSES; i += RT_COST_BLOCK) {
-        const unsigned n = blk[i];
-        if (n) atomicAdd(&s_base[i % RT_COST_CLASSES], n);
+    if (lane < RT_COST_CLASSES) { // lane = class, warp w sums the rows w, w + 8, ... of the blocks before this one
+        unsigned n = 0;
+        for (int b = warp; b < (int)blockIdx.x; b += RT_COST_BLOCK / 32) n += blk[b * RT_COST_CLASSES + lane];
+        if (n) atomicAdd(&s_base[lane], n);
     }
     __syncthreads();
     if (threadIdx.x < RT_COST_CLASSES) {
