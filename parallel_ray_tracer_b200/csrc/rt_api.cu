@@ -69,6 +69,11 @@ struct Dev {
     unsigned* cost_blk = nullptr;
     int cost_cur = 0;
     bool cost_valid = false;
+    // heaviest pixel and total steps of the last finished frame that recorded them, for the occupancy of chain-bound frames
+    bool slot_stat[RT_FRAME_SLOTS] = {};
+    int slot_key[RT_FRAME_SLOTS][5] = {};
+    unsigned long long stat_max = 0, stat_total = 0;
+    int stat_key[5] = {0, 0, 0, 0, 0};
     int cost_key[5] = {0, 0, 0, 0, 0}; // width, height, spp, part_index, part_count
     RtPathRec* drain_queue[RT_FRAME_SLOTS] = {}; // tail hand-off queue per frame slot (render_kernel.cuh: drain_kernel)
     size_t drain_cap[RT_FRAME_SLOTS] = {};
@@ -213,7 +218,8 @@ __device__ __forceinline__ int cost_class(unsigned v)
 
 __global__ void __launch_bounds__(RT_COST_BLOCK) tile_class_kernel(const unsigned short* __restrict__ cost, int width, int height, int tiles_x,
                                                                     const unsigned* __restrict__ tile_list, int n_tiles, unsigned char* __restrict__ cls,
-                                                                    unsigned* __restrict__ hdr, unsigned* __restrict__ hdr_old, unsigned* __restrict__ blk)
+                                                                    unsigned* __restrict__ hdr, unsigned* __restrict__ hdr_old, unsigned* __restrict__ blk,
+                                                                    unsigned long long* __restrict__ stat)
 {
     __shared__ unsigned s_cnt[RT_COST_CLASSES];
     // the header the placement kernel of the previous frame has finished with becomes the next frame's: zero it here (saves
@@ -223,20 +229,25 @@ __global__ void __launch_bounds__(RT_COST_BLOCK) tile_class_kernel(const unsigne
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, per = (n_tiles + gridDim.x - 1) / gridDim.x;
     const int k0 = blockIdx.x * per, k1 = min(k0 + per, n_tiles);
+    unsigned long long w_sum = 0; // (lane 0 of each warp)
+    unsigned w_max = 0;
     for (int k = k0 + warp; k < k1; k += RT_COST_BLOCK / 32) { // one 16x8 tile per warp: lane = row (lane >> 2), 4 columns from (lane & 3) * 4
         const unsigned tile = tile_list[k];
         const int y = (int)(tile / (unsigned)tiles_x) * RT_TILE_H + (lane >> 2), x0 = (int)(tile % (unsigned)tiles_x) * RT_TILE_W + ((lane & 3) << 2);
-        unsigned m = 0;
+        unsigned m = 0, s = 0;
         if (y < height)
             for (int j = 0; j < 4; j++)
-                if (x0 + j < width) m = max(m, (unsigned)cost[(size_t)y * width + x0 + j]);
+                if (x0 + j < width) { const unsigned v = cost[(size_t)y * width + x0 + j]; m = max(m, v); s += v; }
         m = __reduce_max_sync(0xffffffffu, m);
+        s = __reduce_add_sync(0xffffffffu, s);
+        w_sum += s; w_max = max(w_max, m);
         if (lane == 0) {
             const int c = min(cost_class(m), RT_COST_CLASSES - 1);
             cls[k] = (unsigned char)c;
             atomicAdd(&s_cnt[c], 1u);
         }
     }
+    if (stat && lane == 0 && w_max) { atomicMax(&stat[0], (unsigned long long)w_max); atomicAdd(&stat[1], w_sum); }
     __syncthreads();
     if (threadIdx.x < RT_COST_CLASSES) {
         const unsigned n = s_cnt[threadIdx.x];
@@ -766,22 +777,36 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         f.tri_id = (p->aov_mask & RT_AOV_TRI_ID) ? S.tri_id : nullptr;
         f.depth = (p->aov_mask & RT_AOV_DEPTH) ? S.depth : nullptr;
 
+        RtLaunchCfg cf = cfg;
+        const bool track_cost = p->mode == RT_MODE_FAST && cfg.wide != 0 && p->schedule >= 0 && p->bounces > 0 && D.n_tiles > 0;
+        const int key[5] = {w, h, p->spp, p->part_index, part_count};
+        if (track_cost && p->ctas_per_sm <= 0 && cfg.block_threads == 128 && D.stat_total > 0 && std::memcmp(key, D.stat_key, sizeof key) == 0) {
+            // A frame whose heaviest pixel takes much longer than an even share of the frame's steps is bound by that pixel's
+            // dependent chain, and the chain runs faster with fewer warps competing for the SM's issue slots (and with the
+            // registers of the roomier kernel instance); a frame with work for every lane wants all the warps.
+            // r = heaviest pixel / (total steps / lane slots of the default occupancy); thresholds from the sweep in
+            // profiles/r02_ab_occupancy_ratio.jsonl (full frames and partitions of three scenes).  The bytes of a frame do not
+            // depend on the grid.
+            static const bool adaptive = [] { const char* e = std::getenv("RT_ADAPTIVE_CTAS"); return !e || std::atoi(e) != 0; }();
+            const double even = (double)D.stat_total / ((double)D.sm_count * cfg.min_ctas * cfg.block_threads);
+            const double r = (double)D.stat_max / even;
+            const int want = r < 1.15 ? 6 : r < 3.0 ? 5 : r < 3.5 ? 4 : r < 6.0 ? 3 : 2;
+            if (adaptive && want < cf.min_ctas) cf.min_ctas = want;
+        }
         int occ = 0, regs = 0;
-        cudaError_t e = (p->mode == RT_MODE_STRICT) ? rt_occupancy_strict(cfg, &occ, &regs) : rt_occupancy_fast(cfg, &occ, &regs);
+        cudaError_t e = (p->mode == RT_MODE_STRICT) ? rt_occupancy_strict(cf, &occ, &regs) : rt_occupancy_fast(cf, &occ, &regs);
         CK(c, e);
         if (occ < 1) return fail(c, RT_ERR_CUDA, "rt_render: kernel does not fit on an SM");
-        RtLaunchCfg cf = cfg;
         // persistent: one resident wave; ctas_per_sm may ask for FEWER resident CTAs than fit (fewer warps per SM
         // run each warp faster, which shortens the tail of long paths at equal throughput)
-        cf.grid = D.sm_count * (p->ctas_per_sm > 0 ? std::min(occ, p->ctas_per_sm) : occ);
+        const int ctas = (p->ctas_per_sm > 0 || cf.min_ctas < cfg.min_ctas) ? std::min(occ, cf.min_ctas) : occ;
+        cf.grid = D.sm_count * ctas;
         const int warps_needed = (D.n_tiles * (RT_TILE_PIXELS / 32) + (cf.block_threads / 32) - 1) / (cf.block_threads / 32);
         if (warps_needed < cf.grid) cf.grid = std::max(warps_needed, 1);
 
         // heaviest tiles first: this frame records per-pixel costs and, when the previous frame had this shape, renders the
         // tiles in the order made from that frame's costs
         f.cost_out = nullptr;
-        const bool track_cost = p->mode == RT_MODE_FAST && cfg.wide != 0 && p->schedule >= 0 && p->bounces > 0 && D.n_tiles > 0;
-        const int key[5] = {w, h, p->spp, p->part_index, part_count};
         if (track_cost) {
             if (D.cost_px < npx || D.sorted_cap < (size_t)D.n_tiles) { // (re)allocate
                 CK(c, cudaStreamSynchronize(D.stream));
@@ -833,8 +858,13 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         if (track_cost) { // order the tiles for the next frame of this shape (inside this frame's timed window)
             const int nb = std::min(D.sm_count * 4, (D.n_tiles + 7) / 8);
             unsigned* const hdr = D.cost_hdr + RT_COST_HDR * D.cost_cur;
+            // (frame statistics for the occupancy choice below go into two words of the control block that only the opt-in drain
+            // kernel uses otherwise; they reach the host with the ray counters)
+            unsigned long long* const stat = f.drain_k > 0 ? nullptr : ctrl + 5;
             tile_class_kernel<<<nb, RT_COST_BLOCK, 0, D.stream>>>(D.cost, w, h, fa.tiles_x, D.tile_list, D.n_tiles, D.tile_cls, hdr,
-                                                                  D.cost_hdr + RT_COST_HDR * (1 - D.cost_cur), D.cost_blk);
+                                                                  D.cost_hdr + RT_COST_HDR * (1 - D.cost_cur), D.cost_blk, stat);
+            D.slot_stat[slot] = stat != nullptr;
+            std::memcpy(D.slot_key[slot], key, sizeof key);
             tile_place_kernel<<<nb, RT_COST_BLOCK, 0, D.stream>>>(D.tile_list, D.n_tiles, D.tile_cls, hdr, D.cost_blk, D.tile_sorted);
             CK(c, cudaGetLastError());
             launches += 2;
@@ -933,6 +963,7 @@ static int finish_frame(rt_ctx* c, int slot, rt_timing* tm)
             t.rays_shadow += st[1];
             t.inner_visits += st[2];
             t.tri_tests += st[3];
+            if (D.slot_stat[slot]) { D.stat_max = st[5]; D.stat_total = st[6]; std::memcpy(D.stat_key, D.slot_key[slot], sizeof D.stat_key); D.slot_stat[slot] = false; }
             if (st[7]) { // checked build: an index left its array (render_kernel.cuh: RT_BCHECK codes)
                 S.render_pending = false;
                 return fail(c, RT_ERR_STATE, "RT_DEBUG_BOUNDS: check " + std::to_string(st[7]) + " failed on device " + std::to_string(D.id));
