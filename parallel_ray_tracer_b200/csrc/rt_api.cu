@@ -207,7 +207,7 @@ __global__ void unpack_tiles_kernel(uchar4* __restrict__ frame, const uchar4* __
 //   places every block's tiles of a class behind those of the blocks before it — a stable counting sort.
 constexpr int RT_COST_CLASSES = 21;
 constexpr int RT_COST_HDR = 64;
-constexpr int RT_COST_BLOCK = 256;
+constexpr int RT_COST_BLOCK = 1024; // few large blocks: short per-warp loops, and a short prefix over the blocks before
 
 __device__ __forceinline__ int cost_class(unsigned v)
 {
@@ -222,10 +222,13 @@ __global__ void __launch_bounds__(RT_COST_BLOCK) tile_class_kernel(const unsigne
                                                                     unsigned long long* __restrict__ stat)
 {
     __shared__ unsigned s_cnt[RT_COST_CLASSES];
+    __shared__ unsigned s_max;
+    __shared__ unsigned long long s_sum;
     // the header the placement kernel of the previous frame has finished with becomes the next frame's: zero it here (saves
     // a memset per frame; nothing touches it before the next frame's kernels)
     if (blockIdx.x == 0 && threadIdx.x < RT_COST_HDR) hdr_old[threadIdx.x] = 0u;
     if (threadIdx.x < RT_COST_CLASSES) s_cnt[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) { s_max = 0u; s_sum = 0ull; }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, per = (n_tiles + gridDim.x - 1) / gridDim.x;
     const int k0 = blockIdx.x * per, k1 = min(k0 + per, n_tiles);
@@ -247,13 +250,14 @@ __global__ void __launch_bounds__(RT_COST_BLOCK) tile_class_kernel(const unsigne
             atomicAdd(&s_cnt[c], 1u);
         }
     }
-    if (stat && lane == 0 && w_max) { atomicMax(&stat[0], (unsigned long long)w_max); atomicAdd(&stat[1], w_sum); }
+    if (lane == 0 && w_max) { atomicMax(&s_max, w_max); atomicAdd(&s_sum, w_sum); }
     __syncthreads();
     if (threadIdx.x < RT_COST_CLASSES) {
         const unsigned n = s_cnt[threadIdx.x];
         blk[blockIdx.x * RT_COST_CLASSES + threadIdx.x] = n;
         if (n) atomicAdd(&hdr[threadIdx.x], n);
     }
+    if (stat && threadIdx.x == 0 && s_max) { atomicMax(&stat[0], (unsigned long long)s_max); atomicAdd(&stat[1], s_sum); }
 }
 
 __global__ void __launch_bounds__(RT_COST_BLOCK) tile_place_kernel(const unsigned* __restrict__ tile_list, int n_tiles, const unsigned char* __restrict__ cls,
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(RT_COST_BLOCK) tile_place_kernel(const unsigne
         for (int j = threadIdx.x + 1; j < RT_COST_CLASSES; j++) above += hdr[j];   // heavier classes come first
         s_base[threadIdx.x] += above;
     }
-    for (int b = k0; b < k1; b += RT_COST_BLOCK) { // 256 list entries at a time, kept in list order within a class
+    for (int b = k0; b < k1; b += RT_COST_BLOCK) { // one block-full of list entries at a time, kept in list order within a class
         for (int i = threadIdx.x; i < (RT_COST_BLOCK / 32) * RT_COST_CLASSES; i += RT_COST_BLOCK) (&s_wcnt[0][0])[i] = 0u;
         __syncthreads();
         const int k = b + threadIdx.x;
@@ -856,7 +860,7 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
             launches++;
         }
         if (track_cost) { // order the tiles for the next frame of this shape (inside this frame's timed window)
-            const int nb = std::min(D.sm_count * 4, (D.n_tiles + 7) / 8);
+            const int nb = std::min(D.sm_count, (D.n_tiles + RT_COST_BLOCK / 32 - 1) / (RT_COST_BLOCK / 32));
             unsigned* const hdr = D.cost_hdr + RT_COST_HDR * D.cost_cur;
             // (frame statistics for the occupancy choice below go into two words of the control block that only the opt-in drain
             // kernel uses otherwise; they reach the host with the ray counters)

@@ -7,7 +7,7 @@ python bench.py --steps 30 --warmup 5 > gpurun_out/${T}_bench_n1.json 2> gpurun_
 $CMD > gpurun_out/${T}_plain.log 2> gpurun_out/${T}_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${T}_launches.csv $CMD > gpurun_out/${T}_ncu_l.log 2>&1
 $CMD > gpurun_out/${T}_plain2.log 2> gpurun_out/${T}_plain2.err &&
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:rt_fast::render_kernel<.int.128, .int.6, .bool.0, .bool.1, .int.1>" -s 6 -c 1 \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:rt_fast::render_kernel<.int.128, .int.[0-9], .bool.0, .bool.1, .int.1>" -s 8 -c 1 \
     -f -o gpurun_out/${T}_prof_car_only $CMD > gpurun_out/${T}_ncu_f.log 2>&1
 $CMD > gpurun_out/${T}_plain3.log 2> gpurun_out/${T}_plain3.err &&
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:rt_fast::render_kernel<.int.128, .int.8, .bool.0, .bool.1, .int.0>" -s 4 -c 1 \
