@@ -582,9 +582,17 @@ int rt_create_gpu(rt_scene* s, int heuristic, const int* devices, int ndev, int 
     rt_scene_desc d;
     rt::GpuTree tree;
     const bool tiny = s->n_tris() <= 2; // the root is a leaf: flatten.cpp's synthetic root node
+    const bool timing = std::getenv("RT_TIMING") != nullptr;
+    auto t_mark = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        const auto now = std::chrono::steady_clock::now();
+        if (timing) std::fprintf(stderr, "[rt_create_gpu] %-28s %.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_mark).count());
+        t_mark = now;
+    };
     if (!tiny) {
         rc = rt::gpu_build_bvh(*s, (heuristic & RT_BVH_REFBIN) ? 1 : 0, devices[0], stats, download_tree ? nullptr : &tree);
         if (rc) return rc;
+        lap("BVH build (incl. upload)");
     } else if ((rc = rt_scene_build_bvh(s, heuristic))) return rc;
     if (tiny || download_tree || tree.fell_back) { // the tree is on the host (asked for, or degenerate input): host flatten
         if ((rc = rt_scene_view(s, &d))) return rc;
@@ -596,16 +604,18 @@ int rt_create_gpu(rt_scene* s, int heuristic, const int* devices, int ndev, int 
     rt::flatten_small(d, small);
     rt::DeviceFlat df;
     std::string err;
-    const auto t_f0 = std::chrono::steady_clock::now();
+    lap("host scene view");
     rc = rt::flatten_gpu(tree, s->tri_mat.empty() ? nullptr : s->tri_mat.data(), s->n_mats(), df, err);
-    if (std::getenv("RT_TIMING")) std::fprintf(stderr, "[rt_create_gpu] device-side flatten %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_f0).count());
+    lap("device-side flatten");
     tree.release();
+    lap("release of the build's arrays");
     if (rc) {
         cudaFree(df.nodes); cudaFree(df.nodes4); cudaFree(df.nodes8); cudaFree(df.tris); cudaFree(df.shade); cudaFree(df.leaf_cnt);
         return fail(nullptr, rc, "rt_create_gpu: " + err);
     }
     rc = create_common(small, &df, devices, ndev, out);
     cudaFree(df.nodes); cudaFree(df.nodes4); cudaFree(df.nodes8); cudaFree(df.tris); cudaFree(df.shade); cudaFree(df.leaf_cnt); // (null once adopted)
+    lap("context (adopts the arrays)");
     return rc;
     });
 }
