@@ -792,9 +792,10 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         f.depth = (p->aov_mask & RT_AOV_DEPTH) ? S.depth : nullptr;
 
         RtLaunchCfg cf = cfg;
-        const bool track_cost = p->mode == RT_MODE_FAST && cfg.wide != 0 && p->schedule >= 0 && p->bounces > 0 && D.n_tiles > 0;
+        static const bool cost_all = [] { const char* e = std::getenv("RT_COST_2WIDE"); return !e || std::atoi(e) != 0; }();
+        const bool track_cost = p->mode == RT_MODE_FAST && (cfg.wide != 0 || cost_all) && p->schedule >= 0 && p->bounces > 0 && D.n_tiles > 0;
         const int key[5] = {w, h, p->spp, p->part_index, part_count};
-        if (track_cost && p->ctas_per_sm <= 0 && cfg.block_threads == 128 && D.stat_total > 0 && std::memcmp(key, D.stat_key, sizeof key) == 0) {
+        if (track_cost && cfg.wide != 0 && p->ctas_per_sm <= 0 && cfg.block_threads == 128 && D.stat_total > 0 && std::memcmp(key, D.stat_key, sizeof key) == 0) {
             // A frame whose heaviest pixel takes much longer than an even share of the frame's steps is bound by that pixel's
             // dependent chain, and the chain runs faster with fewer warps competing for the SM's issue slots (and with the
             // registers of the roomier kernel instance); a frame with work for every lane wants all the warps.

@@ -7,7 +7,9 @@ scene, w, h = (sys.argv[1], int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv)
 trav = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 ctas = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 order_mode = sys.argv[6] if len(sys.argv) > 6 else "raster"   # raster | heavy_first | light_first
-sched = int(sys.argv[7]) if len(sys.argv) > 7 else 0           # rt_render_params.schedule (0 = heaviest pixels first, -1 = chunk order)
+sched = int(sys.argv[7]) if len(sys.argv) > 7 else 0           # rt_render_params.schedule (0 = heaviest tiles first, -1 = spatial order)
+parts = int(sys.argv[8]) if len(sys.argv) > 8 else 1           # one rank's share of a tile-split frame: part_index of part_count
+part = int(sys.argv[9]) if len(sys.argv) > 9 else 0
 sc = rt.Scene.load_rtsc(f'tests/golden/scenes/{scene}.rtsc').build_bvh(6); ctx = rt.Context(sc, [0])
 if order_mode != "raster":
     # cost proxy per 16x8 tile: first-hit pixels (scripts/exp_tile_order.py)
@@ -19,15 +21,15 @@ if order_mode != "raster":
     cost = pad.reshape(tyn, 8, txn, 16).sum(axis=(1, 3)).reshape(-1)[tl].astype(int)
     ctx.set_tile_order(tl[np.argsort(-cost if order_mode == "heavy_first" else cost, kind="stable")])
 ctx.warp_trace(True)
-p = rt.default_params(width=w, height=h, aov_mask=rt.RT_AOV_WORK, traversal=trav, ctas_per_sm=ctas, schedule=sched)
-pn = rt.default_params(width=w, height=h, traversal=trav, ctas_per_sm=ctas, schedule=sched)
+p = rt.default_params(width=w, height=h, aov_mask=rt.RT_AOV_WORK, traversal=trav, ctas_per_sm=ctas, schedule=sched, part_count=parts, part_index=part)
+pn = rt.default_params(width=w, height=h, traversal=trav, ctas_per_sm=ctas, schedule=sched, part_count=parts, part_index=part)
 for _ in range(30): ctx.render_frame(pn)
 plain = np.median([ctx.render_frame(pn).kernel_ms[0] for _ in range(20)])
 for _ in range(4): tm = ctx.render_frame(p)
 t = ctx.warp_trace(True).astype(np.float64)
 t0 = t[:, 0].min(); start = t[:, 0] - t0; empty = t[:, 1] - t0; exit_ = t[:, 2] - t0
 dur = exit_.max()
-out = {"order": order_mode, "schedule": sched, "scene": scene, "w": w, "h": h, "trav": trav, "kernel_ms_plain": float(plain), "kernel_ms_traced": float(tm.kernel_ms[0]), "warps": len(t), "dur_ns": dur,
+out = {"order": order_mode, "schedule": sched, "parts": parts, "part": part, "scene": scene, "w": w, "h": h, "trav": trav, "kernel_ms_plain": float(plain), "kernel_ms_traced": float(tm.kernel_ms[0]), "warps": len(t), "dur_ns": dur,
        "queue_empty_ns": {"min": empty[empty > 0].min(), "median": float(np.median(empty[empty > 0]))},
        "exit_ns": {"mean": exit_.mean(), "p50": float(np.median(exit_)), "p90": float(np.percentile(exit_, 90)), "p99": float(np.percentile(exit_, 99)), "max": dur},
        "iters": {"mean": t[:, 4].mean(), "p90": float(np.percentile(t[:, 4], 90)), "max": t[:, 4].max(), "sum": t[:, 4].sum()},

@@ -32,7 +32,7 @@ def same(a, b):
 
 
 @pytest.mark.parametrize("scene", ["car_only", "car_boxed", "soup2k"])
-@pytest.mark.parametrize("traversal", [3, 4])
+@pytest.mark.parametrize("traversal", [2, 3, 4])
 def test_heavy_first_frames_equal_chunk_order_frames(rt, gpu_scenes, scene, traversal):
     sc, _ = gpu_scenes[scene]
     ctx = rt.Context(sc, [0])          # a context of its own: the cost history starts empty
