@@ -151,7 +151,7 @@ enum { /* rt_render_params.traversal */
     RT_TRAVERSAL_DEFAULT = 0,
     RT_TRAVERSAL_PLAIN = 1,       /* while-while in the reference's visit order */
     RT_TRAVERSAL_SPECULATIVE = 2, /* 2-wide tree, postponed leaves: same image, more lanes busy */
-    RT_TRAVERSAL_WIDE = 3,        /* 4-wide collapse of the reference tree + postponed leaves */
+    RT_TRAVERSAL_WIDE = 3,        /* 4-wide tree made from the reference tree + postponed leaves */
     RT_TRAVERSAL_WIDE8 = 4        /* compressed 8-wide collapse (96-byte nodes, 8-bit outward-rounded child boxes, csrc/wide8.h) */
 };
 

@@ -47,7 +47,7 @@
 
 struct RtDeviceScene {
     const float4* nodes;
-    const float4* nodes4;   // 4-wide collapse (fast build), 8 x float4 per node
+    const float4* nodes4;   // 4-wide tree (fast build; wide8.h: build_wide4), 8 x float4 per node
     const uint4*  nodes8;   // compressed 8-wide collapse (fast build), 96 bytes = 6 x uint4 per node (wide8.h); may be null
     const float4* tris;
     const float4* shade;

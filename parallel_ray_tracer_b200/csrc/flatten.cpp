@@ -208,95 +208,35 @@ int flatten_scene(const rt_scene_desc& d, FlatScene& out, std::string& err)
     });
     if (bad.load()) { err = "BVH leaf range out of bounds"; return RT_ERR_INVALID; }
 
-    // ---- 4-wide collapse for the fast build: every other level of the reference tree is skipped ----
-    // A BVH4 node holds the (up to four) grandchildren of a reference inner node — a child that is a leaf stays
-    // as it is — in left-to-right order, boxes as SoA rows: minx[4] miny[4] minz[4] maxx[4] maxy[4] maxz[4]
-    // refs[4] pad[4] = 128 bytes.  Leaf references and triangle slots are shared with the 2-wide layout.
-    {
-        std::vector<int32_t> idx4(nb, -1);
-        std::vector<uint32_t> order4;
-        std::vector<uint32_t> stack4;
-        auto kids_of = [&](uint32_t n2, uint32_t* kids) -> int {
-            int c = 0;
-            for (int w = 0; w < 2; w++) {
-                const uint32_t ch = (uint32_t)d.bvh[n2].idx + (uint32_t)w;
-                if (is_inner(d.bvh[ch])) { kids[c++] = (uint32_t)d.bvh[ch].idx; kids[c++] = (uint32_t)d.bvh[ch].idx + 1; }
-                else kids[c++] = ch;
-            }
-            return c;
-        };
-        if (is_inner(d.bvh[0])) stack4.push_back(0);
-        while (!stack4.empty()) {
-            const uint32_t n2 = stack4.back();
-            stack4.pop_back();
-            idx4[n2] = (int32_t)order4.size();
-            order4.push_back(n2);
-            uint32_t kids[4];
-            const int c = kids_of(n2, kids);
-            for (int i = c - 1; i >= 0; i--)
-                if (is_inner(d.bvh[kids[i]])) stack4.push_back(kids[i]);
+    // ---- 4-wide FP32 tree for the fast build (wide8.h: build_wide4) ----
+    // A node holds up to four children of a reference subtree — its frontier after expanding the inner child of largest surface
+    // area until four children exist — as SoA rows: cx[4] cy[4] cz[4] hx[4] hy[4] hz[4] (centre, half extent) refs[4] pad[4] =
+    // 128 bytes; reference subtrees of <= wide4_leaf_max() triangles are one leaf.  Leaf references and triangle slots are
+    // shared with the 2-wide layout.  (Until the middle of round 2 the tree was the collapse of every other reference level:
+    // a third of its slots were empty, profiles/r02_notes.md §9.)
+    if (!is_inner(d.bvh[0])) {
+        // the root itself is a leaf: one node whose only child holds it, in a box no ray can miss
+        out.nodes4.resize(32);
+        float* q = out.nodes4.data();
+        for (int i = 0; i < 12; i++) q[i] = INFINITY; // empty slot: centre at +inf, half extent 0, ref NONE
+        for (int i = 12; i < 24; i++) q[i] = 0.0f;
+        const int32_t none = RT_REF_NONE_HOST;
+        for (int i = 0; i < 4; i++) std::memcpy(&q[24 + i], &none, 4);
+        for (int i = 28; i < 32; i++) q[i] = 0.0f;
+        int32_t ref = RT_REF_NONE_HOST;
+        leaf_ref(d.bvh[0], ref);
+        if (ref != RT_REF_NONE_HOST) {
+            for (int a = 0; a < 3; a++) { q[4 * a] = 0.0f; q[12 + 4 * a] = 1e30f; }
+            std::memcpy(&q[24], &ref, 4);
         }
-        const size_t n4 = order4.empty() ? 1 : order4.size();
-        out.nodes4.resize(32 * n4);
-        parallel_for(n4, [&](size_t lo, size_t hi) {
-            for (size_t k = lo; k < hi; k++) { // all slots empty by default: centre at +inf, half extent 0, ref NONE
-                float* q = &out.nodes4[32 * k];
-                for (int i = 0; i < 12; i++) q[i] = INFINITY;
-                for (int i = 12; i < 24; i++) q[i] = 0.0f;
-                const int32_t none = RT_REF_NONE_HOST;
-                for (int i = 0; i < 4; i++) std::memcpy(&q[24 + i], &none, 4);
-                for (int i = 28; i < 32; i++) q[i] = 0.0f;
-            }
-        });
-        auto put4 = [&](float* q, int slot, const rt_bvh_node& c, int32_t ref) {
-            if (ref == RT_REF_NONE_HOST) return;
-            // centre and half extent (render_kernel.cuh: box_key4); the half extent is rounded up so that
-            // [centre - half, centre + half] contains the builder's box (flatten_gpu.cu: nodes4_kernel does the same)
-            for (int a = 0; a < 3; a++) {
-                float ctr, half;
-                box_center_half(c.min[a], c.max[a], ctr, half);
-                q[4 * a + slot] = ctr; q[12 + 4 * a + slot] = half;
-            }
-            std::memcpy(&q[24 + slot], &ref, 4);
-        };
-        if (order4.empty()) {
-            int32_t ref = RT_REF_NONE_HOST;
-            leaf_ref(d.bvh[0], ref);
-            rt_bvh_node all = d.bvh[0];
-            for (int a = 0; a < 3; a++) { all.min[a] = -1e30f; all.max[a] = 1e30f; }
-            put4(out.nodes4.data(), 0, all, ref);
-        }
-        // records (independent per node) ...
-        parallel_for(order4.size(), [&](size_t lo, size_t hi) {
-            for (size_t k = lo; k < hi; k++) {
-                uint32_t kids[4];
-                const int c = kids_of(order4[k], kids);
-                float* q = &out.nodes4[32 * k];
-                for (int i = 0; i < c; i++) {
-                    const rt_bvh_node& ch = d.bvh[kids[i]];
-                    int32_t ref = RT_REF_NONE_HOST;
-                    if (is_inner(ch)) ref = idx4[kids[i]];
-                    else if (!leaf_ref(ch, ref)) { bad.store(1); ref = RT_REF_NONE_HOST; }
-                    put4(q, i, ch, ref);
-                }
-            }
-        });
-        if (bad.load()) { err = "BVH leaf range out of bounds"; return RT_ERR_INVALID; }
-        // ... and the stack need of a ray (bottom-up): at a node with c live children one is entered and at most c-1 stay pushed
-        std::vector<int32_t> need4(n4, 0);
-        for (size_t k = order4.size(); k-- > 0;) { // children have larger indices than their parent (pre-order)
-            const float* q = &out.nodes4[32 * k];
-            int live = 0, deepest = 0;
-            for (int i = 0; i < 4; i++) {
-                int32_t ref;
-                std::memcpy(&ref, &q[24 + i], 4);
-                if (ref == RT_REF_NONE_HOST) continue;
-                live++;
-                if (ref >= 0) deepest = std::max(deepest, need4[(size_t)ref]);
-            }
-            need4[k] = std::max(live - 1, 0) + deepest;
-        }
-        out.stack_need4 = (order4.empty() ? 0 : need4[0]) + 3; // + sentinel, postponed leaf, slack
+        out.stack_need4 = 3;
+    } else {
+        std::vector<float> n4;
+        int need = 0;
+        const int rc4 = build_wide4(d.bvh, (uint32_t)nb, wide4_leaf_max(), n4, &need);
+        if (rc4) { err = "BVH child index out of range (4-wide tree)"; return rc4; }
+        out.nodes4.assign(n4.begin(), n4.end());
+        out.stack_need4 = need + 3; // + sentinel, postponed leaf, slack
     }
     // ---- compressed 8-wide collapse (wide8.h): the fast build's default tree ----
     {

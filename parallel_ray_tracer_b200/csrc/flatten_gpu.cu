@@ -112,100 +112,84 @@ __global__ void nodes_kernel(int n_nodes, int n_tris, const rt_bvh_node* __restr
     atomicMax(&flags->max_depth, (int)depth[v]);
 }
 
-// 4-wide records: the (up to four) grandchildren of an even-depth inner node, a leaf child staying as it is
-__global__ void nodes4_kernel(int n_nodes, int n_tris, const rt_bvh_node* __restrict__ nodes, const unsigned char* __restrict__ depth,
-                              const int* __restrict__ idx4_of, float4* __restrict__ out, unsigned char* __restrict__ lvl4, FlatFlags* flags)
-{
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_nodes) return;
-    const rt_bvh_node b = nodes[v];
-    if (!is_inner(b) || (depth[v] & 1)) return;
-    const int k4 = idx4_of[(b.idx - 1) >> 1];
-    int kids[4], c = 0;
-    for (int w = 0; w < 2; w++) {
-        const int ch = b.idx + w;
-        const rt_bvh_node cn = nodes[ch];
-        if (is_inner(cn)) { kids[c++] = cn.idx; kids[c++] = cn.idx + 1; }
-        else kids[c++] = ch;
-    }
-    float q[32];
-    for (int i = 0; i < 12; i++) q[i] = INFINITY; // empty slot: centre +inf, half extent 0
-    for (int i = 12; i < 24; i++) q[i] = 0.f;
-    for (int i = 0; i < 4; i++) q[24 + i] = __int_as_float(RT_REF_NONE);
-    for (int i = 28; i < 32; i++) q[i] = 0.f;
-    for (int i = 0; i < c; i++) {
-        const rt_bvh_node kn = nodes[kids[i]];
-        int ref;
-        if (is_inner(kn)) ref = idx4_of[(kn.idx - 1) >> 1];
-        else ref = child_ref(kn, n_tris, nullptr, flags) /* counts were recorded by nodes_kernel */;
-        if (ref == RT_REF_NONE) continue;
-        for (int a = 0; a < 3; a++) { // centre and half extent, bit for bit flatten.h: box_center_half (this file: -fmad=false)
-            const float mn = kn.min[a], mx = kn.max[a];
-            const float ctr = mn * 0.5f + mx * 0.5f;
-            const float up = mx - ctr, dn = ctr - mn;
-            float h = up > dn ? up : dn;
-            if (h > 0.0f && h < 3.0e38f) h = __uint_as_float(__float_as_uint(h) + 1u);
-            q[4 * a + i] = ctr; q[12 + 4 * a + i] = h;
-        }
-        q[24 + i] = __int_as_float(ref);
-    }
-    float4* o = out + 8 * (size_t)k4;
-    for (int i = 0; i < 8; i++) o[i] = make_float4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
-    lvl4[k4] = (unsigned char)(depth[v] >> 1);
-}
-
-// stack need of a ray on the 4-wide tree, one level per launch, deepest first: a node with c live children enters one
-// and leaves at most c - 1 pushed (flatten.cpp: need4)
-__global__ void need4_kernel(int n4, const float4* __restrict__ nodes4, const unsigned char* __restrict__ lvl4, int* __restrict__ need4, int level)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n4 || lvl4[k] != level) return;
-    const float4 r = nodes4[8 * (size_t)k + 6];
-    const int ref[4] = {__float_as_int(r.x), __float_as_int(r.y), __float_as_int(r.z), __float_as_int(r.w)};
-    int live = 0, deepest = 0;
-    for (int i = 0; i < 4; i++) {
-        if (ref[i] == RT_REF_NONE) continue;
-        live++;
-        if (ref[i] >= 0) deepest = max(deepest, need4[ref[i]]);
-    }
-    need4[k] = max(live - 1, 0) + deepest;
-}
-
 // ---- compressed 8-wide tree (wide8.h), level by level exactly as wide8.cpp builds it on the host ----
 // pass A: inner children per node of the level
-__global__ void w8_count_kernel(int n, int leaf_max, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, int* __restrict__ n_inner)
+__global__ void w8_count_kernel(int n, int leaf_max, int width, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, int* __restrict__ n_inner)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     rt::W8Child ch[8];
-    const int c = rt::w8_expand(bvh, level[i], leaf_max, ch);
+    const int c = rt::w8_expand(bvh, level[i], leaf_max, ch, width);
     int k = 0;
     for (int j = 0; j < c; j++) k += ch[j].inner;
     n_inner[i] = k;
 }
 // pass B: the next level's node list (inner children in slot order, the order their indices are assigned in) and the
 // level's plan: per (node, slot) the reference node whose box the slot holds (-1 = empty) and the slot's final reference
-__global__ void w8_plan_kernel(int n, int leaf_max, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, const int* __restrict__ offset,
+// (width 8: slots by octant order, wide8.h; width 4 — the FP32 4-wide tree, build_wide4 — children stay in expansion order)
+__global__ void w8_plan_kernel(int n, int leaf_max, int width, const unsigned* __restrict__ level, const rt_bvh_node* __restrict__ bvh, const int* __restrict__ offset,
                                unsigned next_base, unsigned* __restrict__ next, int* __restrict__ plan_node, int* __restrict__ plan_ref)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     rt::W8Child ch[8];
     int slot_of[8];
-    const int c = rt::w8_expand(bvh, level[i], leaf_max, ch);
-    rt::w8_assign_slots(ch, c, slot_of);
-    for (int s = 0; s < 8; s++) { plan_node[8 * (size_t)i + s] = -1; plan_ref[8 * (size_t)i + s] = RT_REF_NONE; }
+    const int c = rt::w8_expand(bvh, level[i], leaf_max, ch, width);
+    if (width == 8) rt::w8_assign_slots(ch, c, slot_of);
+    else for (int j = 0; j < 8; j++) slot_of[j] = j;
+    for (int s = 0; s < width; s++) { plan_node[width * (size_t)i + s] = -1; plan_ref[width * (size_t)i + s] = RT_REF_NONE; }
     int m = 0;
-    for (int s = 0; s < 8; s++)
+    for (int s = 0; s < width; s++)
         for (int j = 0; j < c; j++)
             if (slot_of[j] == s) {
-                plan_node[8 * (size_t)i + s] = ch[j].bnode;
+                plan_node[width * (size_t)i + s] = ch[j].bnode;
                 if (ch[j].inner) {
-                    plan_ref[8 * (size_t)i + s] = (int)(next_base + (unsigned)offset[i] + (unsigned)m);
+                    plan_ref[width * (size_t)i + s] = (int)(next_base + (unsigned)offset[i] + (unsigned)m);
                     next[offset[i] + m] = (unsigned)ch[j].bnode;
                     m++;
-                } else plan_ref[8 * (size_t)i + s] = rt::w8_leaf_ref(ch[j].first, ch[j].cnt);
+                } else plan_ref[width * (size_t)i + s] = rt::w8_leaf_ref(ch[j].first, ch[j].cnt);
             }
+}
+// the records of one level of the 4-wide FP32 tree (device_layout.h: nodes4), one thread per (node, slot): centre and half extent of
+// the slot's box bit for bit as flatten.h: box_center_half computes them (this file: -fmad=false), the reference, the pad
+__global__ void w4_encode_kernel(int n, const rt_bvh_node* __restrict__ bvh, const int* __restrict__ plan_node, const int* __restrict__ plan_ref,
+                                 unsigned base, float* __restrict__ nodes4)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = tid >> 2, slot = tid & 3;
+    if (i >= n) return;
+    const int mine = plan_node[4 * (size_t)i + slot], ref = plan_ref[4 * (size_t)i + slot];
+    float* q = nodes4 + 32 * (size_t)(base + (unsigned)i);
+    const bool live = mine >= 0 && ref != RT_REF_NONE;
+    for (int a = 0; a < 3; a++) {
+        float ctr = INFINITY, h = 0.f; // empty slot: centre +inf, half extent 0
+        if (live) {
+            const float mn = bvh[mine].min[a], mx = bvh[mine].max[a];
+            ctr = mn * 0.5f + mx * 0.5f;
+            const float up = mx - ctr, dn = ctr - mn;
+            h = up > dn ? up : dn;
+            if (h > 0.0f && h < 3.0e38f) h = __uint_as_float(__float_as_uint(h) + 1u);
+        }
+        q[4 * a + slot] = ctr; q[12 + 4 * a + slot] = h;
+    }
+    q[24 + slot] = __int_as_float(live ? ref : RT_REF_NONE);
+    q[28 + slot] = 0.f;
+}
+// stack need of a ray on the 4-wide tree, one level per launch, deepest first: a node with c live children enters one and leaves at
+// most c - 1 pushed (wide8.cpp: build_wide4)
+__global__ void w4_need_kernel(int n, unsigned base, const float* __restrict__ nodes4, int* __restrict__ need4)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* q = nodes4 + 32 * (size_t)(base + (unsigned)i);
+    int live = 0, deepest = 0;
+    for (int s = 0; s < 4; s++) {
+        const int ref = __float_as_int(q[24 + s]);
+        if (ref == RT_REF_NONE) continue;
+        live++;
+        if (ref >= 0) deepest = max(deepest, need4[ref]);
+    }
+    need4[base + (unsigned)i] = max(live - 1, 0) + deepest;
 }
 // pass C: the records of the level, one thread per (node, slot): the node's grid from the union of its children's boxes
 // (recomputed by each of the eight threads), the slot's own six bytes and reference, the header by slot 0
@@ -280,12 +264,11 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
     if (n < 1 || nn < 3) { err = "flatten_gpu: the tree has no inner node"; return RT_ERR_INVALID; }
     const size_t n_inner = (size_t)(nn - 1) / 2; // every split allocated two nodes
     CKF(cudaSetDevice(t.device));
-    Buf tris, shade, nodes, nodes4, leaf_cnt, is_even, idx4, lvl4, need4, flags, mat, scan_tmp;
+    Buf tris, shade, nodes, nodes4, leaf_cnt, is_even, need4, flags, mat;
     CKF(tris.alloc((size_t)n * 64));
     CKF(shade.alloc((size_t)n * 16));
     CKF(nodes.alloc(n_inner * 64));
     CKF(is_even.alloc(n_inner * 4));
-    CKF(idx4.alloc((n_inner + 1) * 4));
     CKF(flags.alloc(sizeof(FlatFlags)));
     CKF(cudaMemset(flags.p, 0, sizeof(FlatFlags)));
     if (host_tri_mat) {
@@ -310,27 +293,89 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
         CKF(cudaGetLastError());
     }
     stage("tris / shade / nodes");
-    // 4-wide node indices: exclusive scan of the even-depth flags in pre-order
-    size_t tmp_bytes = 0;
-    CKF(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, is_even.as<int>(), idx4.as<int>(), (int)n_inner));
-    CKF(scan_tmp.alloc(tmp_bytes));
-    CKF(cub::DeviceScan::ExclusiveSum(scan_tmp.p, tmp_bytes, is_even.as<int>(), idx4.as<int>(), (int)n_inner));
-    int last_idx = 0, last_flag = 0;
-    CKF(cudaMemcpy(&last_idx, idx4.as<int>() + (n_inner - 1), 4, cudaMemcpyDeviceToHost));
-    CKF(cudaMemcpy(&last_flag, is_even.as<int>() + (n_inner - 1), 4, cudaMemcpyDeviceToHost));
-    const int n4 = last_idx + last_flag;
-    CKF(nodes4.alloc((size_t)n4 * 128));
-    CKF(lvl4.alloc((size_t)n4));
-    CKF(need4.alloc((size_t)n4 * 4));
-    CKF(cudaMemset(need4.p, 0, (size_t)n4 * 4));
-    nodes4_kernel<<<(nn + B - 1) / B, B>>>(nn, n, t.nodes, t.depth, idx4.as<int>(), nodes4.as<float4>(), lvl4.as<unsigned char>(), flags.as<FlatFlags>());
-    for (int level = fl.max_depth / 2; level >= 0; level--)
-        need4_kernel<<<(n4 + B - 1) / B, B>>>(n4, nodes4.as<float4>(), lvl4.as<unsigned char>(), need4.as<int>(), level);
-    CKF(cudaGetLastError());
+    // ---- the two wide trees of the fast build, level by level exactly as wide8.cpp builds them on the host: first the node lists
+    // of all levels (count inner children, exclusive scan, plan every (node, slot)), then the records ----
+    {   // keep freed blocks in the pool between levels instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, t.device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    const bool dbg = std::getenv("RT_SYNC_DEBUG") != nullptr; // name the failing kernel (no compute-sanitizer on the pool)
+    struct Levels {
+        std::vector<Buf> lists, plan_nodes, plan_refs; // per level: node list, (node, slot) plan
+        std::vector<int> sizes;
+        size_t n_nodes = 0;
+        int depth = 0;
+    };
+    Buf tmp;
+    size_t tmp_cap = 0;
+    auto plan_levels = [&](int width, int leaf_max, Levels& L) -> int {
+#define CKL(what) do { if (dbg) { cudaError_t e__ = cudaDeviceSynchronize(); if (e__ != cudaSuccess) { err = std::string("flatten_gpu: ") + what + " (width " + std::to_string(width) + ", level " + std::to_string(lv) + "): " + cudaGetErrorString(e__); return RT_ERR_CUDA; } } } while (0)
+        L.lists.reserve(72); L.plan_nodes.reserve(72); L.plan_refs.reserve(72); // (Buf is not movable: no reallocation; <= 66 levels, checked below)
+        L.lists.emplace_back();
+        CKF(L.lists[0].alloc_pooled(4));
+        CKF(cudaMemset(L.lists[0].p, 0, 4)); // level 0 = {reference node 0}
+        L.sizes.push_back(1);
+        size_t done = 0; // nodes of the levels before this one
+        for (int lv = 0; L.sizes[lv] > 0; lv++) {
+            if (lv > 64) { err = "flatten_gpu: wide tree deeper than 64 levels"; return RT_ERR_INVALID; }
+            const int m = L.sizes[lv];
+            Buf c2, off;
+            CKF(c2.alloc_pooled(((size_t)m + 1) * 4));
+            CKF(cudaMemset(c2.p, 0, ((size_t)m + 1) * 4));
+            w8_count_kernel<<<(m + 127) / 128, 128>>>(m, leaf_max, width, L.lists[lv].as<unsigned>(), t.nodes, c2.as<int>());
+            CKL("w8_count_kernel");
+            CKF(off.alloc_pooled(((size_t)m + 1) * 4));
+            size_t need = 0;
+            CKF(cub::DeviceScan::ExclusiveSum(nullptr, need, c2.as<int>(), off.as<int>(), m + 1));
+            if (need > tmp_cap) { if (tmp.p) cudaFreeAsync(tmp.p, 0); tmp.p = nullptr; CKF(tmp.alloc_pooled(need)); tmp_cap = need; }
+            CKF(cub::DeviceScan::ExclusiveSum(tmp.p, need, c2.as<int>(), off.as<int>(), m + 1));
+            int total = 0;
+            CKF(cudaMemcpy(&total, off.as<int>() + m, 4, cudaMemcpyDeviceToHost));
+            L.lists.emplace_back(); L.plan_nodes.emplace_back(); L.plan_refs.emplace_back();
+            CKF(L.lists[lv + 1].alloc_pooled((size_t)std::max(total, 1) * 4));
+            CKF(L.plan_nodes[lv].alloc_pooled((size_t)m * 4 * width));
+            CKF(L.plan_refs[lv].alloc_pooled((size_t)m * 4 * width));
+            w8_plan_kernel<<<(m + 127) / 128, 128>>>(m, leaf_max, width, L.lists[lv].as<unsigned>(), t.nodes, off.as<int>(), (unsigned)(done + (size_t)m),
+                                                     L.lists[lv + 1].as<unsigned>(), L.plan_nodes[lv].as<int>(), L.plan_refs[lv].as<int>());
+            CKF(cudaGetLastError());
+            CKL("w8_plan_kernel");
+            L.sizes.push_back(total);
+            done += (size_t)m;
+            L.n_nodes += (size_t)m;
+            L.depth++;
+        }
+#undef CKL
+        return RT_OK;
+    };
+    // 4-wide FP32 tree (wide8.h: build_wide4)
+    Levels L4;
+    int rc_l = plan_levels(4, rt::wide4_leaf_max(), L4);
+    if (rc_l) return rc_l;
+    const size_t n4 = L4.n_nodes;
+    CKF(nodes4.alloc(n4 * 128));
+    CKF(need4.alloc(n4 * 4));
+    {
+        size_t base = 0;
+        std::vector<size_t> bases;
+        for (int lv = 0; lv < L4.depth; lv++) {
+            const int m = L4.sizes[lv];
+            bases.push_back(base);
+            w4_encode_kernel<<<(4 * m + 127) / 128, 128>>>(m, t.nodes, L4.plan_nodes[lv].as<int>(), L4.plan_refs[lv].as<int>(), (unsigned)base, nodes4.as<float>());
+            base += (size_t)m;
+        }
+        for (int lv = L4.depth - 1; lv >= 0; lv--) {
+            const int m = L4.sizes[lv];
+            w4_need_kernel<<<(m + B - 1) / B, B>>>(m, (unsigned)bases[lv], nodes4.as<float>(), need4.as<int>());
+        }
+        CKF(cudaGetLastError());
+    }
     int need_root = 0;
     CKF(cudaMemcpy(&need_root, need4.p, 4, cudaMemcpyDeviceToHost));
-    stage("4-wide nodes");
-    // ---- compressed 8-wide tree: first the node lists of all levels (sizes), then the records ----
+    stage("4-wide tree");
+    // compressed 8-wide tree
     Buf nodes8;
     size_t n8 = 0;
     int depth8 = 0;
@@ -347,65 +392,20 @@ int rt::flatten_gpu(const GpuTree& t, const uint32_t* host_tri_mat, uint32_t n_m
         CKF(nodes8.alloc(n8 * 96));
         CKF(rt::staged_h2d(nodes8.p, w8.words.data(), n8 * 96, 0));
     } else {
-        std::vector<Buf> lists, plan_nodes, plan_refs;   // per level: node list, (node, slot) plan
-        std::vector<int> sizes;
-        {   // keep freed blocks in the pool between levels instead of returning them to the driver
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, t.device) == cudaSuccess) {
-                unsigned long long keep = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-        }
-        lists.reserve(72); plan_nodes.reserve(72); plan_refs.reserve(72); // (Buf is not movable: no reallocation; <= 66 levels, checked below)
-        lists.emplace_back();
-        CKF(lists[0].alloc_pooled(4));
-        CKF(cudaMemset(lists[0].p, 0, 4)); // level 0 = {reference node 0}
-        sizes.push_back(1);
-        Buf tmp;
-        size_t tmp_cap = 0;
-        const int leaf_max = rt::wide8_leaf_max();
-        const bool dbg = std::getenv("RT_SYNC_DEBUG") != nullptr; // name the failing kernel (no compute-sanitizer on the pool)
-#define CKL(what) do { if (dbg) { cudaError_t e__ = cudaDeviceSynchronize(); if (e__ != cudaSuccess) { err = std::string("flatten_gpu: ") + what + " (level " + std::to_string(lv) + "): " + cudaGetErrorString(e__); return RT_ERR_CUDA; } } } while (0)
-        size_t done = 0; // nodes of the levels before this one
-        for (int lv = 0; sizes[lv] > 0; lv++) {
-            if (lv > 64) { err = "flatten_gpu: 8-wide tree deeper than 64 levels"; return RT_ERR_INVALID; }
-            const int m = sizes[lv];
-            Buf c2, off;
-            CKF(c2.alloc_pooled(((size_t)m + 1) * 4));
-            CKF(cudaMemset(c2.p, 0, ((size_t)m + 1) * 4));
-            w8_count_kernel<<<(m + 127) / 128, 128>>>(m, leaf_max, lists[lv].as<unsigned>(), t.nodes, c2.as<int>());
-            CKL("w8_count_kernel");
-            CKF(off.alloc_pooled(((size_t)m + 1) * 4));
-            size_t need = 0;
-            CKF(cub::DeviceScan::ExclusiveSum(nullptr, need, c2.as<int>(), off.as<int>(), m + 1));
-            if (need > tmp_cap) { if (tmp.p) cudaFreeAsync(tmp.p, 0); tmp.p = nullptr; CKF(tmp.alloc_pooled(need)); tmp_cap = need; }
-            CKF(cub::DeviceScan::ExclusiveSum(tmp.p, need, c2.as<int>(), off.as<int>(), m + 1));
-            int total = 0;
-            CKF(cudaMemcpy(&total, off.as<int>() + m, 4, cudaMemcpyDeviceToHost));
-            lists.emplace_back(); plan_nodes.emplace_back(); plan_refs.emplace_back();
-            CKF(lists[lv + 1].alloc_pooled((size_t)std::max(total, 1) * 4));
-            CKF(plan_nodes[lv].alloc_pooled((size_t)m * 32));
-            CKF(plan_refs[lv].alloc_pooled((size_t)m * 32));
-            w8_plan_kernel<<<(m + 127) / 128, 128>>>(m, leaf_max, lists[lv].as<unsigned>(), t.nodes, off.as<int>(), (unsigned)(done + (size_t)m),
-                                                     lists[lv + 1].as<unsigned>(), plan_nodes[lv].as<int>(), plan_refs[lv].as<int>());
-            CKF(cudaGetLastError());
-            CKL("w8_plan_kernel");
-            sizes.push_back(total);
-            done += (size_t)m;
-            n8 += (size_t)m;
-            depth8++;
-        }
+        Levels L8;
+        rc_l = plan_levels(8, rt::wide8_leaf_max(), L8);
+        if (rc_l) return rc_l;
+        n8 = L8.n_nodes; depth8 = L8.depth;
         stage("8-wide: levels (count/scan/plan)");
         CKF(nodes8.alloc(n8 * 96));
         size_t base = 0;
         for (int lv = 0; lv < depth8; lv++) {
-            const int m = sizes[lv];
-            w8_encode_kernel<<<(8 * m + 127) / 128, 128>>>(m, t.nodes, plan_nodes[lv].as<int>(), plan_refs[lv].as<int>(), (unsigned)base, nodes8.as<unsigned>());
-            CKL("w8_encode_kernel");
+            const int m = L8.sizes[lv];
+            w8_encode_kernel<<<(8 * m + 127) / 128, 128>>>(m, t.nodes, L8.plan_nodes[lv].as<int>(), L8.plan_refs[lv].as<int>(), (unsigned)base, nodes8.as<unsigned>());
+            if (dbg) { cudaError_t e__ = cudaDeviceSynchronize(); if (e__ != cudaSuccess) { err = std::string("flatten_gpu: w8_encode_kernel (level ") + std::to_string(lv) + "): " + cudaGetErrorString(e__); return RT_ERR_CUDA; } }
             base += (size_t)m;
         }
         CKF(cudaGetLastError());
-#undef CKL
     }
     CKF(cudaDeviceSynchronize());
 

@@ -8,7 +8,7 @@ struct RtLaunchCfg {
     int min_ctas;       // __launch_bounds__ second argument: caps registers/thread
     bool work_counters; // RT_AOV_WORK build (counts inner visits and triangle tests)
     bool speculative;   // fast build: speculative traversal (postponed leaves)
-    int wide;           // fast build: 0 = the reference's 2-wide tree, 1 = its 4-wide collapse, 2 = compressed 8-wide (both imply speculative)
+    int wide;           // fast build: 0 = the reference's 2-wide tree, 1 = the 4-wide tree made from it, 2 = compressed 8-wide (both imply speculative)
     int grid;           // number of persistent CTAs
 };
 

@@ -94,7 +94,7 @@ RT_W8_HD inline int32_t w8_leaf_ref(int32_t first, int32_t cnt)
 
 // The frontier of reference node `root` (an inner node): up to 8 children, in the order the expansion leaves them
 // (left to right in the reference tree).  Empty leaves of the reference tree (tr_len == 0 && idx == 0) are dropped.
-RT_W8_HD inline int w8_expand(const rt_bvh_node* bvh, uint32_t root, int leaf_max, W8Child* out)
+RT_W8_HD inline int w8_expand(const rt_bvh_node* bvh, uint32_t root, int leaf_max, W8Child* out, int width = 8)
 {
     int n = 0;
     auto put = [&](int at, uint32_t b) {
@@ -111,7 +111,7 @@ RT_W8_HD inline int w8_expand(const rt_bvh_node* bvh, uint32_t root, int leaf_ma
     if (!empty(l)) put(n++, l);
     if (!empty(l + 1)) put(n++, l + 1);
     for (;;) {
-        if (n >= 8) break;
+        if (n >= width) break;
         int best = -1;
         double best_a = -1.0;
         for (int i = 0; i < n; i++)
@@ -289,6 +289,15 @@ struct Wide8Tree {
     size_t n_nodes() const { return words.size() / kWide8Words; }
 };
 int build_wide8(const rt_bvh_node* bvh, uint32_t bvh_len, int leaf_max, Wide8Tree& out);
+
+// The 4-wide FP32 tree of the fast build (device_layout.h: nodes4, 32 floats per node: centre and half extent of four child boxes,
+// SoA, + four references) by the SAME expansion with width 4: a node rooted at a reference inner node holds the frontier reached by
+// replacing the inner child of largest surface area by its two children until four children exist or none is inner — nodes are
+// full wherever the subtree allows it, where the collapse of every other level left a third of the slots empty.  Reference
+// subtrees of at most leaf_max triangles become one leaf (contiguous slots).  Nodes are numbered breadth-first; *stack_need is the
+// number of traversal-stack entries a ray can need below the root (a node with c children enters one and leaves c - 1 pushed).
+int build_wide4(const rt_bvh_node* bvh, uint32_t bvh_len, int leaf_max, std::vector<float>& nodes4, int* stack_need);
+int wide4_leaf_max(); // 3, or RT_W4_LEAF_MAX from the environment, clamped to [1, RT_W8_LEAF_CAP] (sweep: profiles/r02_ab_w4_adaptive.log)
 int wide8_leaf_max(); // the knob: kWide8LeafMaxDefault or RT_W8_LEAF_MAX from the environment, clamped to [2, RT_W8_LEAF_CAP]
 
 } // namespace rt

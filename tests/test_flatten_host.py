@@ -78,48 +78,81 @@ def test_layout_rules(rt, scene):
     assert f["max_depth"] <= 32 and f["stack_need4"] >= 3
 
 
+def expand4(bvh, root, leaf_max, width=4):
+    """csrc/wide8.h: w8_expand restated on the reference node array: the frontier of reference inner node `root` after expanding
+    the inner child of largest surface area until `width` children exist; a subtree of <= leaf_max triangles is one leaf.
+    Returns [(reference node, is_inner, first_slot, count)] left to right."""
+    def inner(b): return bvh["tr_len"][b] == 0 and bvh["idx"][b] != 0
+    def empty(b): return bvh["tr_len"][b] == 0 and bvh["idx"][b] == 0
+    def small(b):
+        stack, total, first = [b], 0, -1
+        while stack:
+            x = stack.pop()
+            if inner(x):
+                stack += [int(bvh["idx"][x]) + 1, int(bvh["idx"][x])]
+            elif bvh["tr_len"][x] > 0:
+                if first < 0: first = int(bvh["idx"][x])
+                total += int(bvh["tr_len"][x])
+                if total > leaf_max: return None
+        return (max(first, 0), total)
+    def child(b):
+        if inner(b):
+            s = small(b)
+            return (b, True, 0, 0) if s is None else (b, False, s[0], s[1])
+        return (b, False, int(bvh["idx"][b]), int(bvh["tr_len"][b]))
+    def area(b):
+        d = bvh["max"][b].astype(np.float64) - bvh["min"][b].astype(np.float64)
+        return d[0] * d[1] + d[1] * d[2] + d[2] * d[0]
+    l = int(bvh["idx"][root])
+    out = [child(b) for b in (l, l + 1) if not empty(b)]
+    while len(out) < width:
+        cand = [(area(c[0]), -i) for i, c in enumerate(out) if c[1]]
+        if not cand: break
+        best = -max(cand)[1]                      # largest area, first of equals
+        c = int(bvh["idx"][out[best][0]])
+        kids = [child(b) for b in (c, c + 1) if not empty(b)]
+        out[best:best + 1] = kids
+    return out
+
+
 @pytest.mark.parametrize("scene", SCENES)
-def test_four_wide_collapse_matches_the_two_wide_records(rt, scene):
-    f, _ = flat_of(rt, scene)
-    nodes, r2 = f["nodes"].reshape(-1, 16), refs2(f)
+def test_four_wide_tree_is_the_area_ordered_expansion_of_the_reference_tree(rt, scene):
+    f, a = flat_of(rt, scene)
+    bvh = a["bvh_nodes"].view(np.dtype([("min", "<f4", 3), ("max", "<f4", 3), ("tr_len", "<i4"), ("idx", "<i4")]))
     n4 = f["nodes4"].reshape(-1, 32)
     r4 = n4[:, 24:28].view(np.int32)
-
-    def box2(k, w):
-        return (nodes[k, [0, 1, 2]], nodes[k, [3, 4, 5]]) if w == 0 else (nodes[k, [6, 7, 8]], nodes[k, [9, 10, 11]])
-
-    # walk both trees together from the roots: a 4-wide node holds the grandchildren of a 2-wide node, a leaf child as it is
-    stack, visited = [(0, 0)], 0
-    while stack:
-        k2, k4 = stack.pop()
-        visited += 1
-        kids = []
-        for w in (0, 1):
-            ref = r2[k2, w]
-            if ref >= 0:
-                kids += [(r2[ref, 0], box2(ref, 0)), (r2[ref, 1], box2(ref, 1))]
-            else:
-                kids.append((ref, box2(k2, w)))
-        slot = 0
-        for i, (ref, (mn, mx)) in enumerate(kids):
-            if ref == REF_NONE:
-                assert r4[k4, i] == REF_NONE
-                continue
-            # centre / half extent (csrc/flatten.h: box_center_half): contains the 2-wide record's box, at most 2 ulp wider
-            c, h = n4[k4, [0 + i, 4 + i, 8 + i]].astype(np.float64), n4[k4, [12 + i, 16 + i, 20 + i]].astype(np.float64)
-            lo, hi = mn.astype(np.float64), mx.astype(np.float64)
-            assert (c - h <= lo).all() and (c + h >= hi).all()
-            slack = 4 * np.spacing(np.maximum(np.maximum(np.abs(lo), np.abs(hi)), 1e-30).astype(np.float32)).astype(np.float64)
-            assert (lo - (c - h) <= slack).all() and ((c + h) - hi <= slack).all()
-            assert ((h == 0) == (lo == hi)).all()
-            if ref >= 0:
-                stack.append((int(ref), int(r4[k4, i])))
-            else:
-                assert r4[k4, i] == ref
-            slot += 1
-        for i in range(len(kids), 4):
-            assert r4[k4, i] == REF_NONE and np.isinf(n4[k4, i]) and n4[k4, 12 + i] == 0   # empty slot: centre +inf, half 0
-    assert visited == len(n4)
+    if not (bvh["tr_len"][0] == 0 and bvh["idx"][0] != 0):
+        pytest.skip("the root is a leaf: one synthetic node")
+    leaf_max = 3                                  # csrc/wide8.cpp: wide4_leaf_max default
+    # breadth-first, the inner children of a level numbered in order: walk both trees level by level
+    level, base, seen_tris = [0], 0, np.zeros(len(a["tri"]), int)
+    while level:
+        nxt = []
+        next_base = base + len(level)
+        for i, root in enumerate(level):
+            k4 = base + i
+            kids = expand4(bvh, root, leaf_max)
+            assert 1 <= len(kids) <= 4
+            for j, (b, is_in, first, cnt) in enumerate(kids):
+                # centre / half extent (csrc/flatten.h: box_center_half): contains the reference box, at most 2 ulp wider
+                c, h = n4[k4, [0 + j, 4 + j, 8 + j]].astype(np.float64), n4[k4, [12 + j, 16 + j, 20 + j]].astype(np.float64)
+                lo, hi = bvh["min"][b].astype(np.float64), bvh["max"][b].astype(np.float64)
+                assert (c - h <= lo).all() and (c + h >= hi).all()
+                slack = 4 * np.spacing(np.maximum(np.maximum(np.abs(lo), np.abs(hi)), 1e-30).astype(np.float32)).astype(np.float64)
+                assert (lo - (c - h) <= slack).all() and ((c + h) - hi <= slack).all()
+                assert ((h == 0) == (lo == hi)).all()
+                if is_in:
+                    assert r4[k4, j] == next_base + len(nxt)
+                    nxt.append(b)
+                else:
+                    assert cnt >= 1 and r4[k4, j] == ~((first << 4) | min(cnt, 15))
+                    seen_tris[first:first + cnt] += 1
+            for j in range(len(kids), 4):
+                assert r4[k4, j] == REF_NONE and np.isinf(n4[k4, j]) and n4[k4, 12 + j] == 0   # empty slot: centre +inf, half 0
+        base, level = next_base, nxt
+    assert base == len(n4) and (seen_tris == 1).all()
+    # the expansion fills the nodes: at most a quarter of the slots stay empty (the collapse of every other level left a third)
+    assert (r4 != REF_NONE).mean() > 0.75
 
 
 def test_flatten_does_not_depend_on_the_thread_count(rt, monkeypatch):

@@ -4,8 +4,9 @@ checked on the CPU against the sequential definitions they replace.
 1. The reference's in-place partition (cpu/src/bvh.c:244-259), `for i: if left(A[i]) swap(A[i], A[n_left++])`, equals: lefts
    compacted in encounter order; the right element that starts at x ends at the first element of the chain
    x -> posL[x] -> posL[posL[x]] ... that is >= n_left, where posL[r] is the position of the left of rank r.
-2. In the reference's node numbering the k-th inner node in depth-first pre-order has its children at 1 + 2k, and the 4-wide
-   collapse keeps the even-depth inner nodes in the same order.
+2. In the reference's node numbering the k-th inner node in depth-first pre-order has its children at 1 + 2k.
+(The wide trees of the fast build are built level by level from shared host/device code, csrc/wide8.h; their rules are checked by
+tests/test_flatten_host.py and tests/test_wide8_host.py.)
 """
 import numpy as np
 import pytest
@@ -100,17 +101,3 @@ def test_record_index_rules_of_the_device_side_flatten(rt, scene):
     assert len(order) == int(inner.sum())
     for k, v in enumerate(order):
         assert (int(nodes["idx"][v]) - 1) // 2 == k
-    # 4-wide collapse (flatten.cpp: kids_of): its nodes, in its own pre-order, are the even-depth inner nodes in that order
-    order4, stack = [], [0] if inner[0] else []
-    while stack:
-        v = stack.pop()
-        order4.append(v)
-        kids = []
-        for w in (0, 1):
-            ch = int(nodes["idx"][v]) + w
-            kids += [int(nodes["idx"][ch]), int(nodes["idx"][ch]) + 1] if inner[ch] else [ch]
-        for kch in reversed(kids):
-            if inner[kch]:
-                stack.append(kch)
-    even = [v for v in order if depth_of[v] % 2 == 0]
-    assert order4 == even
