@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Same-box A/B of environment settings of ONE library build (kernel ms, median of N frames after >= 150 ms warm-up):
-python scripts/ab_env.py frames NAME=v1,v2,... [k=v render params]   — e.g. RT_REFILL_HEAVY=0,24,28,32"""
+python scripts/ab_env.py frames NAME=v1,v2,... [k=v render params]   — e.g. RT_ADAPTIVE_CTAS=0,1 or RT_W4_LEAF_MAX=2,3,4"""
 import json, os, statistics, subprocess, sys, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Same-box A/B of heaviest-pixels-first scheduling (schedule = 0) against plain chunk order (schedule = -1): median kernel ms
-of N frames after warm-up (the timed window includes the five selection kernels), per workload and traversal."""
+"""Same-box A/B of heaviest-tiles-first scheduling (schedule = 0) against spatial tile order (schedule = -1): median kernel ms
+of N frames after warm-up (the timed window includes the two ordering kernels), per workload and traversal."""
 import json, os, statistics, sys, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
@@ -20,6 +20,6 @@ for scene, w, h, parts in CASES:
                 while time.perf_counter() < t_end:
                     ctx.render_frame(p)
                 ms = [ctx.render_frame(p).kernel_ms[0] for _ in range(frames)]
-                print(json.dumps({"frac": os.environ.get("RT_HEAVY_FRAC", "0.5"), "scene": scene, "w": w, "h": h, "part_count": parts, "traversal": trav, "schedule": sched, "rep": rep,
+                print(json.dumps({"scene": scene, "w": w, "h": h, "part_count": parts, "traversal": trav, "schedule": sched, "rep": rep,
                                   "ms": round(statistics.median(ms), 4), "min": round(min(ms), 4)}), flush=True)
     ctx.close()

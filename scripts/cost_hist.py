@@ -1,4 +1,4 @@
-"""Distribution of the per-pixel traversal cost (steps of the 4-wide kernel) — what the heavy-first scheduler sees."""
+"""Distribution of the per-pixel traversal cost (steps of the 4-wide kernel) — what the heaviest-tiles-first scheduler sees."""
 import sys, json
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent

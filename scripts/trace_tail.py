@@ -46,13 +46,4 @@ for frac in (0.4, 0.5, 0.6, 0.7, 0.8, 0.9):
     per_sm = np.bincount(sm[a], minlength=sm.max() + 1)
     alive.append({"at": frac, "warps_alive": int(a.sum()), "sms_with_work": int((per_sm > 0).sum()), "max_per_sm": int(per_sm.max())})
 out["alive"] = alive
-# warps that took no regular chunk at all worked off the heavy list only (tr_chunks counts regular chunks)
-ho = t[:, 3] == 0
-if ho.any() and (~ho).any():
-    q = lambda v: [float(np.percentile(v, k)) / dur for k in (10, 50, 90, 99, 100)]
-    out["heavy_only_warps"] = {"n": int(ho.sum()), "exit_p10_50_90_99_max": q(exit_[ho]), "iters_mean": float(t[ho, 4].mean()), "iters_max": float(t[ho, 4].max()),
-                               "lanes_per_iter": float((t[ho, 5].sum() + t[ho, 6].sum()) / t[ho, 4].sum())}
-    out["other_warps"] = {"n": int((~ho).sum()), "exit_p10_50_90_99_max": q(exit_[~ho]), "iters_mean": float(t[~ho, 4].mean()), "iters_max": float(t[~ho, 4].max()),
-                          "lanes_per_iter": float((t[~ho, 5].sum() + t[~ho, 6].sum()) / t[~ho, 4].sum()),
-                          "exit_minus_empty_p50_90_max": [float(np.percentile((exit_ - empty)[~ho], k)) for k in (50, 90, 100)]}
 print(json.dumps(out, default=float))
