@@ -185,7 +185,8 @@ typedef struct rt_render_params {
     /* tuning knobs (0 = library default) */
     int32_t   block_threads;    /* threads per CTA */
     int32_t   ctas_per_sm;      /* persistent CTAs per SM */
-    int32_t   refill_threshold; /* leave the traversal loop when fewer lanes than this are active */
+    int32_t   refill_threshold; /* leave the traversal loop when fewer lanes than this are active; 0 = default (fast build: 14 / 16 on
+                                   the 4- / 2-wide tree, 8 on chain-bound frames; strict build: 20) */
     int32_t   traversal;        /* RT_TRAVERSAL_* (fast mode only; strict always walks the reference order) */
     int32_t   frame_flags;      /* RT_FRAME_* */
     int32_t   frame_slot;       /* which of the context's RT_FRAME_SLOTS device frames to render into (frame sequences) */

@@ -734,7 +734,9 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
     fa.cull = (tree8 && p->cull > 0) ? 1 : 0;
     int drain_k = (tree8 && p->drain_k > 0 && 7 * c->depth8 + 1 <= RT_DRAIN_STACK) ? std::min(p->drain_k, 32) : 0;
     if (cfg.work_counters && c->want_trace) drain_k = 0; // the per-warp timeline describes the per-lane kernel alone
-    fa.refill_threshold = p->refill_threshold > 0 ? std::min(p->refill_threshold, 32) : 20;
+    // lanes that have finished their ray wait for phase 1 until fewer than this many lanes of the warp are still tracing (sweep of the
+    // final kernels: profiles/r02_ab_refill_final.log; 20 was the optimum of the round-1 kernels and stays for the strict build)
+    fa.refill_threshold = p->refill_threshold > 0 ? std::min(p->refill_threshold, 32) : (p->mode == RT_MODE_FAST ? (wide ? 14 : 16) : 20);
 
     S.width = w; S.height = h; S.aov_mask = p->aov_mask; S.spp = p->spp; S.flags = p->frame_flags;
     S.part_index = p->part_index; S.part_count = part_count;
@@ -795,18 +797,19 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         static const bool cost_all = [] { const char* e = std::getenv("RT_COST_2WIDE"); return !e || std::atoi(e) != 0; }();
         const bool track_cost = p->mode == RT_MODE_FAST && (cfg.wide != 0 || cost_all) && p->schedule >= 0 && p->bounces > 0 && D.n_tiles > 0;
         const int key[5] = {w, h, p->spp, p->part_index, part_count};
-        if (track_cost && cfg.wide != 0 && p->ctas_per_sm <= 0 && cfg.block_threads == 128 && D.stat_total > 0 && std::memcmp(key, D.stat_key, sizeof key) == 0) {
+        if (track_cost && cfg.wide != 0 && cfg.block_threads == 128 && D.stat_total > 0 && std::memcmp(key, D.stat_key, sizeof key) == 0) {
             // A frame whose heaviest pixel takes much longer than an even share of the frame's steps is bound by that pixel's
             // dependent chain, and the chain runs faster with fewer warps competing for the SM's issue slots (and with the
             // registers of the roomier kernel instance); a frame with work for every lane wants all the warps.
             // r = heaviest pixel / (total steps / lane slots of the default occupancy); thresholds from the sweep in
-            // profiles/r02_ab_occupancy_ratio.jsonl (full frames and partitions of three scenes).  The bytes of a frame do not
-            // depend on the grid.
+            // profiles/r02_ab_occupancy_ratio2.jsonl (full frames and partitions of three scenes, final kernels).  The bytes of a
+            // frame do not depend on the grid.
             static const bool adaptive = [] { const char* e = std::getenv("RT_ADAPTIVE_CTAS"); return !e || std::atoi(e) != 0; }();
-            const double even = (double)D.stat_total / ((double)D.sm_count * cfg.min_ctas * cfg.block_threads);
+            const double even = (double)D.stat_total / ((double)D.sm_count * 6 * cfg.block_threads); // (6 = the wide kernels' default CTAs/SM)
             const double r = (double)D.stat_max / even;
-            const int want = r < 1.15 ? 6 : r < 3.0 ? 5 : r < 3.5 ? 4 : r < 6.0 ? 3 : 2;
-            if (adaptive && want < cf.min_ctas) cf.min_ctas = want;
+            const int want = r < 1.45 ? 6 : r < 3.2 ? 5 : r < 3.55 ? 4 : r < 6.0 ? 3 : 2;
+            if (adaptive && p->ctas_per_sm <= 0 && want < cf.min_ctas) cf.min_ctas = want;
+            if (adaptive && r >= 1.45 && p->refill_threshold <= 0) f.refill_threshold = 8; // chain-bound: phase 1 as rarely as possible
         }
         int occ = 0, regs = 0;
         cudaError_t e = (p->mode == RT_MODE_STRICT) ? rt_occupancy_strict(cf, &occ, &regs) : rt_occupancy_fast(cf, &occ, &regs);
