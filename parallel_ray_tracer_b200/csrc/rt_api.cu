@@ -710,10 +710,10 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
 
     RtLaunchCfg cfg;
     cfg.block_threads = p->block_threads == 64 ? 64 : 128;
-    // Defaults (profiles/r01_notes.md): small frames are bounded by the dependent chain of their longest pixels, which the
-    // wide tree shortens; large frames are throughput-bound.  "Small" is decided from the render parameters ONLY (pixel
-    // samples per GPU), never from what earlier frames did: two frames with equal parameters run the same kernel, on
-    // every rank of a partitioned render.
+    // Defaults: the 4-wide tree at every size (profiles/r02_ab_large.jsonl); frames above 4 M pixel samples per GPU draw their work
+    // from per-SM cursors over macro tiles (throughput-bound: L1 sharing matters), smaller ones from one global counter.  Which
+    // kernel variant runs is decided from the render parameters ONLY, never from what earlier frames did: two frames with equal
+    // parameters run the same traversal code, on every rank of a partitioned render (history only orders tiles and sizes the grid).
     const double px_per_part = (double)w * h * p->spp / (double)(part_count * (int)c->devs.size());
     const bool small_frame = px_per_part <= 4.0e6;
     // fast build: which tree to walk.  The compressed 8-wide tree when the context has one and its depth fits the group
@@ -723,7 +723,7 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
     int wide = 0;
     if (p->traversal == RT_TRAVERSAL_WIDE8) wide = have8 ? 2 : (have4 ? 1 : 0);
     else if (p->traversal == RT_TRAVERSAL_WIDE) wide = have4 ? 1 : 0;
-    else if (p->traversal == RT_TRAVERSAL_DEFAULT) wide = small_frame ? (have4 ? 1 : 0) : 0;
+    else if (p->traversal == RT_TRAVERSAL_DEFAULT) wide = have4 ? 1 : 0; // (until the 4-wide tree was rebuilt in round 2, frames above 4 M pixel samples per GPU walked the 2-wide tree)
     cfg.min_ctas = p->ctas_per_sm > 0 ? p->ctas_per_sm : (cfg.block_threads == 64 ? 12 : (wide ? 6 : 8));
     cfg.work_counters = (p->aov_mask & RT_AOV_WORK) != 0;
     cfg.speculative = p->traversal != RT_TRAVERSAL_PLAIN;
