@@ -715,7 +715,8 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
     // kernel variant runs is decided from the render parameters ONLY, never from what earlier frames did: two frames with equal
     // parameters run the same traversal code, on every rank of a partitioned render (history only orders tiles and sizes the grid).
     const double px_per_part = (double)w * h * p->spp / (double)(part_count * (int)c->devs.size());
-    const bool small_frame = px_per_part <= 4.0e6;
+    static const double smq_px = [] { const char* e = std::getenv("RT_SMQUEUE_PIXELS"); return e ? std::atof(e) : 4.0e6; }();
+    const bool small_frame = px_per_part <= smq_px;
     // fast build: which tree to walk.  The compressed 8-wide tree when the context has one and its depth fits the group
     // stack; RT_TRAVERSAL_* pins a variant (the strict build always walks the reference's own 2-wide order).
     const bool have8 = c->devs[0].nodes8 != nullptr && c->depth8 + 2 <= RT_STACK8_ENTRIES;
@@ -810,6 +811,10 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
             const int want = r < 1.45 ? 6 : r < 3.2 ? 5 : r < 3.55 ? 4 : r < 6.0 ? 3 : 2;
             if (adaptive && p->ctas_per_sm <= 0 && want < cf.min_ctas) cf.min_ctas = want;
             if (adaptive && r >= 1.45 && p->refill_threshold <= 0) f.refill_threshold = 8; // chain-bound: phase 1 as rarely as possible
+            // work distribution: per-SM cursors over macro tiles keep the warps of an SM on neighbouring tiles (L1 sharing: -3 % on
+            // throughput-bound frames of any size) but hand the heaviest tiles out four at a time per SM, which a chain-bound frame
+            // cannot afford (+13 %): profiles/r02_ab_smq_px.log.  Without statistics the frame size decides (above).
+            if (adaptive) f.sm_cursor = r < 1.45 ? ctrl + 8 : nullptr;
         }
         int occ = 0, regs = 0;
         cudaError_t e = (p->mode == RT_MODE_STRICT) ? rt_occupancy_strict(cf, &occ, &regs) : rt_occupancy_fast(cf, &occ, &regs);
