@@ -35,7 +35,9 @@
 #include "rt_b200.h"
 
 #define RT_TILE_PIXELS (RT_TILE_W * RT_TILE_H)
+#ifndef RT_MACRO_CHUNKS
 #define RT_MACRO_CHUNKS 16u /* chunks (8x4 pixels) per macro tile = 4 tiles */
+#endif
 #define RT_MAX_SMS 256
 
 #define RT_REF_NONE ((int)0x80000000)
