@@ -243,3 +243,24 @@ def test_walking_the_flattened_records_finds_the_oracle_hits(rt, oracle_scenes, 
             elif best >= 0:
                 assert abs(best_t - ref["depth"][y, x]) <= 1e-5 * abs(ref["depth"][y, x])
     assert bad == 0
+
+
+def test_center_half_extent_boxes_contain_what_they_encode():
+    """csrc/flatten.h: box_center_half restated in numpy (IEEE float32, round to nearest): the interval [c - h, c + h] evaluated
+    exactly contains [mn, mx] for ordinary, tiny, huge, negative and degenerate intervals, and h == 0 only for mn == mx."""
+    rng = np.random.default_rng(7)
+    mag = np.float32(10.0) ** rng.integers(-30, 30, 200000).astype(np.float32)
+    a = (rng.standard_normal(200000).astype(np.float32) * mag).astype(np.float32)
+    w = np.abs(rng.standard_normal(200000).astype(np.float32)) * np.float32(10.0) ** rng.integers(-35, 30, 200000).astype(np.float32)
+    w[::7] = 0                                                          # flat boxes (axis-aligned triangles)
+    mn, mx = a, (a + w.astype(np.float32)).astype(np.float32)
+    ok = np.isfinite(mn) & np.isfinite(mx) & (mx >= mn)
+    mn, mx = mn[ok], mx[ok]
+    c = (mn * np.float32(0.5) + mx * np.float32(0.5)).astype(np.float32)
+    up, dn = (mx - c).astype(np.float32), (c - mn).astype(np.float32)
+    h = np.maximum(up, dn)
+    bump = (h > 0) & (h < np.float32(3.0e38))
+    h = np.where(bump, (h.view(np.uint32) + np.uint32(1)).view(np.float32), h)
+    c64, h64 = c.astype(np.float64), h.astype(np.float64)
+    assert (c64 - h64 <= mn.astype(np.float64)).all() and (c64 + h64 >= mx.astype(np.float64)).all()
+    assert ((h == 0) == (mn == mx)).all()

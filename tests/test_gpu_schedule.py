@@ -39,6 +39,9 @@ def test_heavy_first_frames_equal_chunk_order_frames(rt, gpu_scenes, scene, trav
     w, h = 960, 540
     plain = render(rt, ctx, w, h, traversal=traversal, schedule=-1)
     assert plain["launches"] == 1
+    with pytest.raises(rt.RtError) as no_history:   # nothing was recorded yet: there is no cost order to show
+        ctx.tile_order(sorted=True)
+    assert no_history.value.code == rt.RT_ERR_STATE
     for k in range(3):                 # frame 0 has no history, frames 1-2 render in cost order
         got = render(rt, ctx, w, h, traversal=traversal)
         assert got["launches"] == 3    # render kernel + the two kernels that order the next frame's tiles
