@@ -10,6 +10,7 @@ struct RtLaunchCfg {
     bool speculative;   // fast build: speculative traversal (postponed leaves)
     int wide;           // fast build: 0 = the reference's 2-wide tree, 1 = the 4-wide tree made from it, 2 = compressed 8-wide (both imply speculative)
     int grid;           // number of persistent CTAs
+    bool park = false;  // fast build, 4-wide tree, no work counters: the instance that keeps the path state in shared memory (8 CTAs/SM)
 };
 
 cudaError_t rt_launch_fast(const RtDeviceScene& sc, const RtFrameArgs& fa, const RtLaunchCfg& cfg, cudaStream_t st);

@@ -27,6 +27,11 @@ static kernel_fn pick(const RtLaunchCfg& c)
     return c.work_counters ? pick<true, false, 0>(c.block_threads, c.min_ctas) : pick<false, false, 0>(c.block_threads, c.min_ctas);
 #else
     if (c.wide == 2) return c.work_counters ? pick<true, true, 2>(c.block_threads, c.min_ctas) : pick<false, true, 2>(c.block_threads, c.min_ctas);
+    if (c.wide == 1 && c.park && !c.work_counters && c.block_threads != 64) {
+        if (c.min_ctas >= 8) return render_kernel<128, 8, false, true, 1, true>;
+        if (c.min_ctas >= 7) return render_kernel<128, 7, false, true, 1, true>;
+        return render_kernel<128, 6, false, true, 1, true>;
+    }
     if (c.wide == 1) return c.work_counters ? pick<true, true, 1>(c.block_threads, c.min_ctas) : pick<false, true, 1>(c.block_threads, c.min_ctas);
     if (c.speculative) return c.work_counters ? pick<true, true, 0>(c.block_threads, c.min_ctas) : pick<false, true, 0>(c.block_threads, c.min_ctas);
     return c.work_counters ? pick<true, false, 0>(c.block_threads, c.min_ctas) : pick<false, false, 0>(c.block_threads, c.min_ctas);

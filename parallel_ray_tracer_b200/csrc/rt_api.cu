@@ -815,6 +815,11 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
             // throughput-bound frames of any size) but hand the heaviest tiles out four at a time per SM, which a chain-bound frame
             // cannot afford (+13 %): profiles/r02_ab_smq_px.log.  Without statistics the frame size decides (above).
             if (adaptive) f.sm_cursor = r < 1.45 ? ctrl + 8 : nullptr;
+            // ... and the kernel instance: with the path state parked in shared memory the 4-wide kernel fits 8 CTAs per SM, which a
+            // throughput-bound frame can use (car_boxed 1080p / 4K -4.4 %, 8K -5.8 %; a share with r = 1.2 loses 3 %: hence r < 1); a
+            // chain-bound frame wants few warps and all registers
+            static const bool park_ok = [] { const char* e = std::getenv("RT_PARK"); return !e || std::atoi(e) != 0; }();
+            if (adaptive && park_ok && r < 1.0 && p->ctas_per_sm <= 0 && !cfg.work_counters) { cf.park = true; cf.min_ctas = 8; }
         }
         int occ = 0, regs = 0;
         cudaError_t e = (p->mode == RT_MODE_STRICT) ? rt_occupancy_strict(cf, &occ, &regs) : rt_occupancy_fast(cf, &occ, &regs);
@@ -822,7 +827,7 @@ static int enqueue_frame(rt_ctx* c, const rt_render_params* p)
         if (occ < 1) return fail(c, RT_ERR_CUDA, "rt_render: kernel does not fit on an SM");
         // persistent: one resident wave; ctas_per_sm may ask for FEWER resident CTAs than fit (fewer warps per SM
         // run each warp faster, which shortens the tail of long paths at equal throughput)
-        const int ctas = (p->ctas_per_sm > 0 || cf.min_ctas < cfg.min_ctas) ? std::min(occ, cf.min_ctas) : occ;
+        const int ctas = (p->ctas_per_sm > 0 || cf.min_ctas != cfg.min_ctas) ? std::min(occ, cf.min_ctas) : occ;
         cf.grid = D.sm_count * ctas;
         const int warps_needed = (D.n_tiles * (RT_TILE_PIXELS / 32) + (cf.block_threads / 32) - 1) / (cf.block_threads / 32);
         if (warps_needed < cf.grid) cf.grid = std::max(warps_needed, 1);
